@@ -1,0 +1,127 @@
+/*
+ * rv_b200.h -- C ABI of the B200-native road-vision preprocessing chain.
+ *
+ * Drop-in boundary for the reference's `src/preprocess` plugin chain.  The reference has no
+ * FFI of its own (it is pure Python calling OpenCV), so every entry point below cites the
+ * reference *Python* interface it replaces (paths relative to /root/reference):
+ *
+ *   rv_chain_u8        PreprocessPipeline.__call__            src/preprocess/pipeline.py:32-45
+ *                      = CLAHEDehaze.__call__                 src/preprocess/ops/clahe_dehaze.py:13-32
+ *                      + MedianDerain.__call__                src/preprocess/ops/median_derain.py:10-14
+ *                      (+ the low-contrast gate               src/preprocess/pipeline.py:24-30,37-40)
+ *   rv_luma_hist       cv2.cvtColor(BGR2LAB|BGR2YCrCb)+split  clahe_dehaze.py:22-23 / :27-28, and the
+ *                      histogram stage of clahe.apply          clahe_dehaze.py:24 / :29
+ *   rv_build_lut       clip/redistribute/CDF stage of cv2.createCLAHE(...).apply   clahe_dehaze.py:19,24,29
+ *   rv_clahe_dehaze    CLAHEDehaze.__call__ alone             clahe_dehaze.py:13-32
+ *   rv_median          MedianDerain.__call__ alone            median_derain.py:10-14
+ *   rv_gray_span       PreprocessPipeline._low_contrast       pipeline.py:24-30
+ *   rv_submit/rv_wait  (new) batched multi-frame entry fed from pinned host buffers; no reference
+ *                      counterpart (the reference loop is one frame in flight, main_preview.py:88-142)
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative rv_status;
+ * rv_last_error(ctx) gives the message.  A context is bound to one CUDA device, owns its streams and
+ * workspaces, and is not thread-safe; different contexts may be used from different threads.
+ * There is NO CPU fallback: without a usable sm_100 device rv_create fails.
+ *
+ * Frames are uint8 BGR, interleaved, `h` rows of `w` pixels, `pitch` bytes between rows
+ * (pitch >= 3*w), `n` frames `frame_stride` bytes apart (0 means h*pitch).
+ */
+#ifndef RV_B200_H
+#define RV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rv_ctx rv_ctx;
+
+enum rv_status {
+    RV_OK = 0,
+    RV_ERR_ARG = -1,      /* bad argument (shape, pitch, ksize, ...) */
+    RV_ERR_CUDA = -2,     /* a CUDA runtime call or kernel failed */
+    RV_ERR_NODEV = -3,    /* no usable sm_100 device */
+    RV_ERR_NOMEM = -4
+};
+
+enum rv_space { RV_SPACE_YCRCB = 0, RV_SPACE_LAB = 1 };
+
+/* where `in`/`out` live */
+enum rv_mem { RV_MEM_HOST = 0, RV_MEM_HOST_PINNED = 1, RV_MEM_DEVICE = 2 };
+
+/* Parameters after the reference's coercions (clahe_dehaze.py:14-17, median_derain.py:11-13):
+ * space exactly "LAB" -> RV_SPACE_LAB else YCrCb; grid = max(2, int(tile_grid));
+ * ksize in {0 (no median), 3, 5, 7, 9}; clip_limit <= 0 disables clipping (plain AHE). */
+typedef struct rv_params {
+    int32_t space;
+    int32_t grid;
+    int32_t ksize;
+    int32_t clahe;          /* 0: skip CLAHEDehaze (median only), 1: run it */
+    double clip_limit;
+    int32_t gate_enable;    /* pipeline.py:37-40: run the chain only if gray span < gate_thresh */
+    int32_t reserved;
+    double gate_thresh;
+} rv_params;
+
+const char *rv_version(void);
+int rv_device_count(void);
+
+int rv_create(int device, rv_ctx **out);
+void rv_destroy(rv_ctx *ctx);
+const char *rv_last_error(const rv_ctx *ctx);
+
+/* tuning knobs: "group_frames" (frames per hist->lut->apply pass, sized for L2 residency),
+ * "chunk_frames" (frames per H2D/compute/D2H pipeline stage for host memory), 0 = automatic;
+ * "kernel_timing" (0/1, see rv_kernel_time). */
+int rv_set_option(rv_ctx *ctx, const char *name, long value);
+/* kernels launched by this context since creation (for bench accounting) */
+long rv_launch_count(const rv_ctx *ctx);
+/* With option "kernel_timing" = 1 every k_luma_hist (which=0), k_build_lut (1) and k_chain (2) launch is
+ * bracketed by CUDA events on its own stream; this returns the summed device time and launch count
+ * since the last reset (synchronises first). */
+int rv_kernel_time(rv_ctx *ctx, int which, double *ms_total, long *launches);
+int rv_kernel_time_reset(rv_ctx *ctx);
+
+/* pinned host memory for the batched entry */
+int rv_alloc_pinned(rv_ctx *ctx, size_t bytes, void **out);
+int rv_free_pinned(rv_ctx *ctx, void *p);
+/* device memory helpers (so that Python callers do not need torch/cupy) */
+int rv_alloc_device(rv_ctx *ctx, size_t bytes, void **out);
+int rv_free_device(rv_ctx *ctx, void *p);
+int rv_memcpy(rv_ctx *ctx, void *dst, const void *src, size_t bytes, int kind /*0 h2d,1 d2h,2 d2d*/);
+int rv_sync(rv_ctx *ctx);
+
+/* The whole chain, synchronous.  `processed` (optional, host, n ints) receives 1 for frames the chain
+ * ran on and 0 for frames the gate skipped (those are copied through unchanged).
+ * `stream` (optional) is a cudaStream_t used for RV_MEM_DEVICE buffers; NULL = the context's stream. */
+int rv_chain_u8(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w,
+                size_t in_pitch, size_t out_pitch, const rv_params *p, int mem_kind,
+                int32_t *processed, void *stream);
+
+/* Asynchronous form for device or pinned buffers: enqueue, return immediately; rv_wait blocks until
+ * everything submitted on this context's own streams has finished.  `stream` (optional cudaStream_t,
+ * RV_MEM_DEVICE only) enqueues on the caller's stream instead, which the caller synchronises. */
+int rv_submit(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w,
+              size_t in_pitch, size_t out_pitch, const rv_params *p, int mem_kind, void *stream);
+int rv_wait(rv_ctx *ctx);
+
+/* Stage-level entry points (parity tests). All synchronous; mem_kind applies to every pointer. */
+/* hist: n*grid*grid*256 int32; luma (optional): n*h*w bytes, packed; span (optional): n*2 int32 {min,max} of gray */
+int rv_luma_hist(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t pitch, int space, int grid,
+                 int32_t *hist, uint8_t *luma, int32_t *gray_minmax, int mem_kind);
+/* lut: n*grid*grid*256 bytes */
+int rv_build_lut(rv_ctx *ctx, const int32_t *hist, int n, int h, int w, int grid, double clip_limit,
+                 uint8_t *lut, int mem_kind);
+int rv_clahe_dehaze(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w,
+                    size_t in_pitch, size_t out_pitch, int space, double clip_limit, int grid, int mem_kind);
+int rv_median(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w,
+              size_t in_pitch, size_t out_pitch, int ksize, int mem_kind);
+/* span: n ints = max(gray) - min(gray) per frame */
+int rv_gray_span(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t pitch, int32_t *span, int mem_kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RV_B200_H */

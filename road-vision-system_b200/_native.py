@@ -1,0 +1,284 @@
+"""ctypes binding of librv_b200.so (include/rv_b200.h).  Plumbing only -- no arithmetic here."""
+import ctypes as C
+import os
+import subprocess
+import threading
+import weakref
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_SO = os.path.join(_CSRC, "librv_b200.so")
+
+SPACE_YCRCB, SPACE_LAB = 0, 1
+MEM_HOST, MEM_PINNED, MEM_DEVICE = 0, 1, 2
+
+
+class RvError(RuntimeError):
+    """A call into the CUDA library failed (no silent CPU fallback exists)."""
+
+
+class Params(C.Structure):
+    """rv_params: parameters *after* the reference's coercions."""
+    _fields_ = [
+        ("space", C.c_int32), ("grid", C.c_int32), ("ksize", C.c_int32), ("clahe", C.c_int32),
+        ("clip_limit", C.c_double), ("gate_enable", C.c_int32), ("reserved", C.c_int32),
+        ("gate_thresh", C.c_double),
+    ]
+
+    @classmethod
+    def make(cls, space="YCrCb", clip_limit=2.0, grid=8, ksize=3, clahe=True, gate=False, gate_thresh=20.0):
+        return cls(SPACE_LAB if space == "LAB" else SPACE_YCRCB, int(grid), int(ksize), 1 if clahe else 0,
+                   float(clip_limit), 1 if gate else 0, 0, float(gate_thresh))
+
+
+def library_path():
+    return _SO
+
+
+def build_library(force=False, verbose=False):
+    """Compile csrc/ for sm_100a with nvcc (works without a GPU)."""
+    srcs = [os.path.join(_CSRC, f) for f in ("rv_b200.cu", "rv_kernels.cuh", "rv_lab_tables.h", "rv_median_net.h")]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "rv_b200.h"))
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    if force or stale:
+        cmd = ["make", "-C", _CSRC, "librv_b200.so"] + (["-B"] if force else [])
+        subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "rv_version": (C.c_char_p, []),
+    "rv_device_count": (C.c_int, []),
+    "rv_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "rv_destroy": (None, [C.c_void_p]),
+    "rv_last_error": (C.c_char_p, [C.c_void_p]),
+    "rv_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_long]),
+    "rv_launch_count": (C.c_long, [C.c_void_p]),
+    "rv_alloc_pinned": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "rv_free_pinned": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rv_alloc_device": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "rv_free_device": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rv_memcpy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "rv_sync": (C.c_int, [C.c_void_p]),
+    "rv_chain_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
+                              C.POINTER(Params), C.c_int, _i32p, C.c_void_p]),
+    "rv_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
+                            C.POINTER(Params), C.c_int, C.c_void_p]),
+    "rv_kernel_time": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]),
+    "rv_kernel_time_reset": (C.c_int, [C.c_void_p]),
+    "rv_wait": (C.c_int, [C.c_void_p]),
+    "rv_luma_hist": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "rv_build_lut": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int]),
+    "rv_clahe_dehaze": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
+                                  C.c_int, C.c_double, C.c_int, C.c_int]),
+    "rv_median": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
+                            C.c_int, C.c_int]),
+    "rv_gray_span": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int]),
+}
+
+
+def load_library():
+    """dlopen the in-tree library and declare every symbol of include/rv_b200.h. Raises if it is missing."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(_SO):
+                raise RvError(f"{_SO} is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+            lib = C.CDLL(_SO)
+            for name, (res, args) in EXPORTS.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def _check_frames(frames):
+    if not isinstance(frames, np.ndarray):
+        raise TypeError("frames must be a numpy.ndarray")
+    if frames.dtype != np.uint8:
+        raise ValueError(f"uint8 BGR frames expected, got dtype {frames.dtype}")
+    if frames.ndim != 4 or frames.shape[3] != 3:
+        raise ValueError(f"(N,H,W,3) uint8 expected, got shape {frames.shape}")
+    if frames.shape[1] < 1 or frames.shape[2] < 1:
+        raise ValueError("empty frame")
+
+
+class Context:
+    """One rv_ctx: a CUDA device, its streams and workspaces. Not thread-safe."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        rc = self._lib.rv_create(int(device), C.byref(h))
+        if rc != 0:
+            raise RvError(f"rv_create(device={device}) failed with {rc}: no usable sm_100 GPU (no CPU fallback)")
+        self._h = h
+        self.device = int(device)
+        self._pinned = {}          # base address -> nbytes
+        self._finalizer = weakref.finalize(self, self._lib.rv_destroy, h)
+
+    # -- plumbing ------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._lib.rv_last_error(self._h)
+            raise (ValueError if rc == -1 else RvError)(f"rv_b200 error {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        self._finalizer()
+
+    def set_option(self, name, value):
+        self._ck(self._lib.rv_set_option(self._h, name.encode(), int(value)))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.rv_launch_count(self._h))
+
+    def sync(self):
+        self._ck(self._lib.rv_sync(self._h))
+
+    def pinned_empty(self, shape, dtype=np.uint8):
+        """A numpy array in page-locked host memory (freed when the array is garbage-collected)."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._ck(self._lib.rv_alloc_pinned(self._h, nbytes, C.byref(p)))
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned[p.value] = nbytes
+        owner = self                # keeps the context alive until its pinned buffers are gone
+
+        def _free(addr=p.value):
+            owner._pinned.pop(addr, None)
+            owner._lib.rv_free_pinned(owner._h, C.c_void_p(addr))
+        weakref.finalize(buf, _free)
+        return arr
+
+    def mem_kind(self, arr):
+        a = arr.ctypes.data
+        for base, n in self._pinned.items():
+            if base <= a < base + max(n, 1):
+                return MEM_PINNED
+        return MEM_HOST
+
+    # -- the chain -----------------------------------------------------------------------
+    def chain(self, frames, params, out=None, processed=None):
+        """rv_chain_u8 over host frames (N,H,W,3) uint8; returns a new (or `out`) array."""
+        _check_frames(frames)
+        if not frames.flags.c_contiguous:
+            frames = np.ascontiguousarray(frames)
+        n, h, w, _ = frames.shape
+        if out is None:
+            out = np.empty_like(frames)
+        elif out.shape != frames.shape or out.dtype != np.uint8 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous uint8 array of the input's shape")
+        kind = MEM_PINNED if (self.mem_kind(frames) == MEM_PINNED and self.mem_kind(out) == MEM_PINNED) else MEM_HOST
+        pp = processed.ctypes.data_as(_i32p) if processed is not None else None
+        self._ck(self._lib.rv_chain_u8(self._h, frames.ctypes.data, out.ctypes.data, n, h, w, 3 * w, 3 * w,
+                                       C.byref(params), kind, pp, None))
+        return out
+
+    def chain_device(self, in_ptr, out_ptr, n, h, w, params, in_pitch=None, out_pitch=None, stream=None):
+        """rv_chain_u8 over device pointers (ints); synchronises the stream before returning."""
+        self._ck(self._lib.rv_chain_u8(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), n, h, w,
+                                       in_pitch or 3 * w, out_pitch or 3 * w, C.byref(params), MEM_DEVICE, None,
+                                       C.c_void_p(stream) if stream else None))
+
+    def submit_device(self, in_ptr, out_ptr, n, h, w, params, in_pitch=None, out_pitch=None, stream=None):
+        """Enqueue the chain over device pointers without synchronising (on `stream`, a cudaStream_t int, if given)."""
+        self._ck(self._lib.rv_submit(self._h, C.c_void_p(in_ptr), C.c_void_p(out_ptr), n, h, w,
+                                     in_pitch or 3 * w, out_pitch or 3 * w, C.byref(params), MEM_DEVICE,
+                                     C.c_void_p(stream) if stream else None))
+
+    def kernel_times(self, reset=False):
+        """{name: (total_ms, launches)} for the hot-path kernels (needs set_option('kernel_timing', 1))."""
+        res = {}
+        for which, name in enumerate(("k_luma_hist", "k_build_lut", "k_chain")):
+            ms, cnt = C.c_double(), C.c_long()
+            self._ck(self._lib.rv_kernel_time(self._h, which, C.byref(ms), C.byref(cnt)))
+            res[name] = (ms.value, cnt.value)
+        if reset:
+            self._ck(self._lib.rv_kernel_time_reset(self._h))
+        return res
+
+    def submit(self, frames, out, params):
+        """Asynchronous rv_submit over pinned host arrays; call wait() before reading `out`."""
+        _check_frames(frames)
+        n, h, w, _ = frames.shape
+        if self.mem_kind(frames) != MEM_PINNED or self.mem_kind(out) != MEM_PINNED:
+            raise ValueError("submit() needs arrays from Context.pinned_empty()")
+        self._ck(self._lib.rv_submit(self._h, frames.ctypes.data, out.ctypes.data, n, h, w, 3 * w, 3 * w,
+                                     C.byref(params), MEM_PINNED, None))
+
+    def wait(self):
+        self._ck(self._lib.rv_wait(self._h))
+
+    # -- stage-level entry points (parity tests) ---------------------------------------------
+    def luma_hist(self, frames, space, grid, want_luma=True, want_gray=False):
+        _check_frames(frames)
+        frames = np.ascontiguousarray(frames)
+        n, h, w, _ = frames.shape
+        hist = np.empty((n, grid * grid, 256), np.int32)
+        luma = np.empty((n, h, w), np.uint8) if want_luma else None
+        mm = np.empty((n, 2), np.int32) if want_gray else None
+        self._ck(self._lib.rv_luma_hist(self._h, frames.ctypes.data, n, h, w, 3 * w,
+                                        SPACE_LAB if space == "LAB" else SPACE_YCRCB, grid, hist.ctypes.data,
+                                        luma.ctypes.data if want_luma else None, mm.ctypes.data if want_gray else None,
+                                        MEM_HOST))
+        return hist, luma, mm
+
+    def build_lut(self, hist, h, w, grid, clip_limit):
+        hist = np.ascontiguousarray(hist, np.int32)
+        n = hist.shape[0]
+        lut = np.empty((n, grid * grid, 256), np.uint8)
+        self._ck(self._lib.rv_build_lut(self._h, hist.ctypes.data, n, h, w, grid, float(clip_limit), lut.ctypes.data, MEM_HOST))
+        return lut
+
+    def clahe_dehaze(self, frames, space, clip_limit, grid):
+        _check_frames(frames)
+        frames = np.ascontiguousarray(frames)
+        n, h, w, _ = frames.shape
+        out = np.empty_like(frames)
+        self._ck(self._lib.rv_clahe_dehaze(self._h, frames.ctypes.data, out.ctypes.data, n, h, w, 3 * w, 3 * w,
+                                           SPACE_LAB if space == "LAB" else SPACE_YCRCB, float(clip_limit), int(grid), MEM_HOST))
+        return out
+
+    def median(self, frames, ksize):
+        _check_frames(frames)
+        frames = np.ascontiguousarray(frames)
+        n, h, w, _ = frames.shape
+        out = np.empty_like(frames)
+        self._ck(self._lib.rv_median(self._h, frames.ctypes.data, out.ctypes.data, n, h, w, 3 * w, 3 * w, int(ksize), MEM_HOST))
+        return out
+
+    def gray_span(self, frames):
+        _check_frames(frames)
+        frames = np.ascontiguousarray(frames)
+        n, h, w, _ = frames.shape
+        span = np.empty(n, np.int32)
+        self._ck(self._lib.rv_gray_span(self._h, frames.ctypes.data, n, h, w, 3 * w, span.ctypes.data, MEM_HOST))
+        return span
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_context(device=None):
+    """Process-wide context per device, created on first use (RV_DEVICE or LOCAL_RANK picks the default GPU)."""
+    if device is None:
+        device = int(os.environ.get("RV_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _default_lock:
+        if device not in _default:
+            _default[device] = Context(device)
+        return _default[device]

@@ -1,0 +1,698 @@
+/*
+ * rv_b200.cu -- C ABI (include/rv_b200.h) over the sm_100a kernels in rv_kernels.cuh.
+ *
+ * Host-side logic of the drop-in boundary: parameter validation, CLAHE geometry
+ * (clahe.cpp semantics), workspaces, the hist -> lut -> apply+median launch
+ * sequence in frame groups sized for L2 residency, and the chunked H2D / compute / D2H
+ * pipeline for host buffers.  No CPU fallback anywhere: if CUDA fails the call fails.
+ */
+#include "../../include/rv_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "rv_kernels.cuh"
+
+using namespace rv;
+
+namespace {
+
+constexpr int NPIPE = 3;
+
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct TimedLaunch {
+    cudaEvent_t a, b;
+    int which;                              // 0 k_luma_hist, 1 k_build_lut, 2 k_chain
+};
+
+}  // namespace
+
+struct rv_ctx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;          // main stream (device buffers, stage-level calls)
+    cudaStream_t pipe[NPIPE] = {};          // H2D / compute / D2H pipeline for host buffers
+    Buf hist[NPIPE + 1], quads[NPIPE + 1], lut[NPIPE + 1], flags[NPIPE + 1], mm[NPIPE + 1];
+    Buf din[NPIPE + 1], dout[NPIPE + 1];
+    Buf scratch;                            // stage-level calls
+    long launches = 0;
+    long group_frames = 0, chunk_frames = 0;
+    long kernel_timing = 0;                 // bracket hist / lut / chain launches with events
+    std::vector<TimedLaunch> timed;         // pending (not yet read) event pairs
+    std::vector<cudaEvent_t> ev_pool;
+    double k_ms[3] = {0, 0, 0};
+    long k_n[3] = {0, 0, 0};
+    char err[512] = {0};
+};
+
+namespace {
+
+int fail(rv_ctx *c, int code, const char *fmt, ...)
+{
+    if (c) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof c->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ctx, RV_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define RV_TRY(call)              \
+    do {                          \
+        int rc_ = (call);         \
+        if (rc_ != RV_OK) return rc_; \
+    } while (0)
+
+int ensure(rv_ctx *ctx, Buf &b, size_t bytes)
+{
+    if (b.cap >= bytes) return RV_OK;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = (bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) return fail(ctx, RV_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    b.cap = want;
+    return RV_OK;
+}
+
+cudaEvent_t get_event(rv_ctx *ctx)
+{
+    if (!ctx->ev_pool.empty()) {
+        cudaEvent_t e = ctx->ev_pool.back();
+        ctx->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct ScopedTiming {                       // records an event pair around one launch when kernel_timing is on
+    rv_ctx *ctx; cudaStream_t st; TimedLaunch t; bool on;
+    ScopedTiming(rv_ctx *c, cudaStream_t s, int which) : ctx(c), st(s), on(c->kernel_timing != 0)
+    {
+        if (on) { t.a = get_event(c); t.b = get_event(c); t.which = which; cudaEventRecord(t.a, st); }
+    }
+    ~ScopedTiming()
+    {
+        if (on) { cudaEventRecord(t.b, st); ctx->timed.push_back(t); }
+    }
+};
+
+// clahe.cpp geometry (A.3): both dimensions are padded when either is not divisible by the grid
+Geo make_geo(int h, int w, int grid)
+{
+    Geo g;
+    g.H = h; g.W = w; g.grid = grid;
+    int eh = h, ew = w;
+    if (w % grid != 0 || h % grid != 0) {
+        ew = w + (grid - w % grid);
+        eh = h + (grid - h % grid);
+    }
+    g.tw = ew / grid;
+    g.th = eh / grid;
+    g.inv_tw = 1.0f / (float)g.tw;
+    g.inv_th = 1.0f / (float)g.th;
+    return g;
+}
+
+int clip_int(double clip_limit, const Geo &g)
+{
+    if (!(clip_limit > 0.0)) return 0;
+    int c = (int)(clip_limit * (double)(g.tw * g.th) / 256.0);
+    return std::max(c, 1);
+}
+
+int check_frames(rv_ctx *ctx, const void *in, const void *out, int n, int h, int w, size_t ipitch, size_t opitch)
+{
+    if (!ctx) return RV_ERR_ARG;
+    if (!in || !out) return fail(ctx, RV_ERR_ARG, "null frame pointer");
+    if (n < 0 || h < 1 || w < 1) return fail(ctx, RV_ERR_ARG, "bad frame shape n=%d h=%d w=%d", n, h, w);
+    if (h > 32768 || w > 32768) return fail(ctx, RV_ERR_ARG, "frame too large (%dx%d)", w, h);
+    if (ipitch < (size_t)3 * w || opitch < (size_t)3 * w) return fail(ctx, RV_ERR_ARG, "pitch smaller than 3*w");
+    return RV_OK;
+}
+
+int check_params(rv_ctx *ctx, const rv_params *p)
+{
+    if (!p) return fail(ctx, RV_ERR_ARG, "null params");
+    if (p->space != RV_SPACE_YCRCB && p->space != RV_SPACE_LAB) return fail(ctx, RV_ERR_ARG, "bad space %d", p->space);
+    if (p->clahe && (p->grid < 2 || p->grid > 256)) return fail(ctx, RV_ERR_ARG, "tile grid %d out of range [2,256]", p->grid);
+    if (!(p->ksize == 0 || p->ksize == 3 || p->ksize == 5 || p->ksize == 7 || p->ksize == 9))
+        return fail(ctx, RV_ERR_ARG, "ksize %d not in {0,3,5,7,9}", p->ksize);
+    return RV_OK;
+}
+
+template <int MODE, int K>
+int launch_chain_t(rv_ctx *ctx, const ChainArgs &a, int n, cudaStream_t st)
+{
+    using S = ChainSmem<MODE, K>;
+    static bool configured[64] = {};
+    if (!configured[ctx->device & 63]) {
+        CK(cudaFuncSetAttribute(k_chain<MODE, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
+        configured[ctx->device & 63] = true;
+    }
+    dim3 grid((a.g.W + TILE_W - 1) / TILE_W, (a.g.H + TILE_H - 1) / TILE_H, n);
+    {
+        ScopedTiming tm(ctx, st, 2);
+        k_chain<MODE, K><<<grid, CHAIN_THREADS, S::total, st>>>(a);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return RV_OK;
+}
+
+template <int MODE>
+int launch_chain_k(rv_ctx *ctx, const ChainArgs &a, int n, int k, cudaStream_t st)
+{
+    switch (k) {
+        case 0: return launch_chain_t<MODE, 0>(ctx, a, n, st);
+        case 3: return launch_chain_t<MODE, 3>(ctx, a, n, st);
+        case 5: return launch_chain_t<MODE, 5>(ctx, a, n, st);
+        case 7: return launch_chain_t<MODE, 7>(ctx, a, n, st);
+        case 9: return launch_chain_t<MODE, 9>(ctx, a, n, st);
+    }
+    return fail(ctx, RV_ERR_ARG, "bad ksize %d", k);
+}
+
+int launch_chain(rv_ctx *ctx, int mode, const ChainArgs &a, int n, int k, cudaStream_t st)
+{
+    if (mode == 0) return launch_chain_k<0>(ctx, a, n, k, st);
+    if (mode == 1) return launch_chain_k<1>(ctx, a, n, k, st);
+    if (k == 0) return fail(ctx, RV_ERR_ARG, "nothing to do (no CLAHE, no median)");
+    return launch_chain_k<2>(ctx, a, n, k, st);
+}
+
+int launch_hist(rv_ctx *ctx, const uint8_t *src, size_t pitch, size_t fstride, const Geo &g, int space, int n,
+                int32_t *hist, uint8_t *luma, int32_t *mm, cudaStream_t st)
+{
+    const int tiles = g.grid * g.grid;
+    CK(cudaMemsetAsync(hist, 0, (size_t)n * tiles * 256 * sizeof(int32_t), st));
+    if (mm) {
+        k_init_minmax<<<(n + 127) / 128, 128, 0, st>>>(mm, n);
+        ctx->launches++;
+    }
+    // enough CTAs to fill the machine a few times over; slices of a tile accumulate with global atomics
+    int slices = 1;
+    const long want = 4L * ctx->sm_count;
+    if ((long)tiles * n < want) slices = (int)std::min<long>((want + (long)tiles * n - 1) / ((long)tiles * n), std::max(1, g.th / 8));
+    const int rps = (g.th + slices - 1) / slices;
+    slices = (g.th + rps - 1) / rps;
+    dim3 grid(slices, tiles, n);
+    {
+        ScopedTiming tm(ctx, st, 0);
+        if (space == RV_SPACE_LAB)
+            k_luma_hist<1><<<grid, HIST_THREADS, 0, st>>>(src, pitch, fstride, g, rps, hist, luma, mm);
+        else
+            k_luma_hist<0><<<grid, HIST_THREADS, 0, st>>>(src, pitch, fstride, g, rps, hist, luma, mm);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return RV_OK;
+}
+
+int launch_lut(rv_ctx *ctx, const int32_t *hist, const Geo &g, double clip_limit, int n, uint8_t *lut, uint32_t *quads,
+               cudaStream_t st)
+{
+    const int clip = clip_int(clip_limit, g);
+    const float lut_scale = 255.0f / (float)(g.tw * g.th);
+    dim3 grid((g.grid + 1) * (g.grid + 1), n);
+    {
+        ScopedTiming tm(ctx, st, 1);
+        k_build_lut<<<grid, 128, 0, st>>>(hist, g.grid, clip, lut_scale, lut, quads);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return RV_OK;
+}
+
+// one group of frames, everything on device, on stream `st`, using workspace set `ws`
+int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs, uint8_t *dout, size_t opitch, size_t ofs,
+              int n, int h, int w, const rv_params *p, cudaStream_t st, int32_t **flags_out)
+{
+    ChainArgs a;
+    a.src = din; a.spitch = ipitch; a.sfstride = ifs;
+    a.dst = dout; a.dpitch = opitch; a.dfstride = ofs;
+    a.quads = nullptr; a.flags = nullptr;
+    if (flags_out) *flags_out = nullptr;
+    if (!p->clahe) {
+        a.g = make_geo(h, w, 2);
+        // gate without CLAHE: still needs the gray span
+        if (p->gate_enable) {
+            RV_TRY(ensure(ctx, ctx->hist[ws], (size_t)n * 4 * 256 * 4));
+            RV_TRY(ensure(ctx, ctx->mm[ws], (size_t)n * 8));
+            RV_TRY(ensure(ctx, ctx->flags[ws], (size_t)n * 4));
+            RV_TRY(launch_hist(ctx, din, ipitch, ifs, a.g, RV_SPACE_YCRCB, n, (int32_t *)ctx->hist[ws].p, nullptr,
+                               (int32_t *)ctx->mm[ws].p, st));
+            k_gate_flags<<<(n + 127) / 128, 128, 0, st>>>((int32_t *)ctx->mm[ws].p, n, (float)p->gate_thresh, (int32_t *)ctx->flags[ws].p);
+            ctx->launches++;
+            a.flags = (int32_t *)ctx->flags[ws].p;
+        }
+        RV_TRY(launch_chain(ctx, 2, a, n, p->ksize, st));
+    } else {
+        const Geo g = make_geo(h, w, p->grid);
+        a.g = g;
+        const size_t tiles = (size_t)g.grid * g.grid, nq = (size_t)(g.grid + 1) * (g.grid + 1);
+        RV_TRY(ensure(ctx, ctx->hist[ws], (size_t)n * tiles * 256 * 4));
+        RV_TRY(ensure(ctx, ctx->quads[ws], (size_t)n * nq * 256 * 4));
+        int32_t *mm = nullptr;
+        if (p->gate_enable) {
+            RV_TRY(ensure(ctx, ctx->mm[ws], (size_t)n * 8));
+            RV_TRY(ensure(ctx, ctx->flags[ws], (size_t)n * 4));
+            mm = (int32_t *)ctx->mm[ws].p;
+        }
+        RV_TRY(launch_hist(ctx, din, ipitch, ifs, g, p->space, n, (int32_t *)ctx->hist[ws].p, nullptr, mm, st));
+        RV_TRY(launch_lut(ctx, (int32_t *)ctx->hist[ws].p, g, p->clip_limit, n, nullptr, (uint32_t *)ctx->quads[ws].p, st));
+        if (p->gate_enable) {
+            k_gate_flags<<<(n + 127) / 128, 128, 0, st>>>(mm, n, (float)p->gate_thresh, (int32_t *)ctx->flags[ws].p);
+            ctx->launches++;
+            a.flags = (int32_t *)ctx->flags[ws].p;
+        }
+        a.quads = (uint32_t *)ctx->quads[ws].p;
+        RV_TRY(launch_chain(ctx, p->space == RV_SPACE_LAB ? 1 : 0, a, n, p->ksize, st));
+    }
+    if (a.flags) {
+        dim3 grid(4, std::min(h, 64), n);
+        k_gate_copy<<<grid, 256, 0, st>>>(din, ipitch, ifs, dout, opitch, ofs, h, 3 * w, a.flags);
+        ctx->launches++;
+        if (flags_out) *flags_out = (int32_t *)ctx->flags[ws].p;
+    }
+    CK(cudaGetLastError());
+    return RV_OK;
+}
+
+long auto_group(const rv_ctx *ctx, int h, int w)
+{
+    if (ctx->group_frames > 0) return ctx->group_frames;
+    const size_t fb = (size_t)3 * w * h;
+    return std::max<long>(1, (long)((40u << 20) / fb));     // input + output of a group stay inside the 126 MB L2
+}
+
+long auto_chunk(const rv_ctx *ctx, int h, int w)
+{
+    if (ctx->chunk_frames > 0) return ctx->chunk_frames;
+    const size_t fb = (size_t)3 * w * h;
+    return std::max<long>(1, (long)((24u << 20) / fb));
+}
+
+int chain_device(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w, size_t ipitch, size_t opitch,
+                 const rv_params *p, int32_t *processed_host, cudaStream_t st)
+{
+    const long G = auto_group(ctx, h, w);
+    const size_t ifs = ipitch * h, ofs = opitch * h;
+    for (int f0 = 0; f0 < n; f0 += (int)G) {
+        const int g = (int)std::min<long>(G, n - f0);
+        int32_t *flags = nullptr;
+        RV_TRY(run_group(ctx, NPIPE, in + (size_t)f0 * ifs, ipitch, ifs, out + (size_t)f0 * ofs, opitch, ofs, g, h, w, p, st, &flags));
+        if (processed_host) {
+            if (flags) {
+                CK(cudaMemcpyAsync(processed_host + f0, flags, (size_t)g * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));      // the workspace is reused by the next group
+            } else {
+                for (int i = 0; i < g; ++i) processed_host[f0 + i] = 1;
+            }
+        }
+    }
+    return RV_OK;
+}
+
+// host buffers: chunks of frames flow H2D -> kernels -> D2H on NPIPE streams
+int chain_host(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w, size_t ipitch, size_t opitch,
+               const rv_params *p, int32_t *processed_host)
+{
+    const long C = std::min<long>(auto_chunk(ctx, h, w), std::max(1, n));
+    const size_t rowb = (size_t)3 * w;
+    const size_t dpitch = (rowb + 15) & ~(size_t)15;
+    const size_t dfs = dpitch * h;
+    for (int i = 0; i < NPIPE; ++i) {
+        RV_TRY(ensure(ctx, ctx->din[i], dfs * C));
+        RV_TRY(ensure(ctx, ctx->dout[i], dfs * C));
+    }
+    int chunk = 0;
+    for (int f0 = 0; f0 < n; f0 += (int)C, ++chunk) {
+        const int s = chunk % NPIPE;
+        const int g = (int)std::min<long>(C, n - f0);
+        cudaStream_t st = ctx->pipe[s];
+        uint8_t *di = (uint8_t *)ctx->din[s].p, *dout = (uint8_t *)ctx->dout[s].p;
+        if (ipitch == dpitch)
+            CK(cudaMemcpyAsync(di, in + (size_t)f0 * ipitch * h, dfs * g, cudaMemcpyHostToDevice, st));
+        else
+            CK(cudaMemcpy2DAsync(di, dpitch, in + (size_t)f0 * ipitch * h, ipitch, rowb, (size_t)h * g, cudaMemcpyHostToDevice, st));
+        int32_t *flags = nullptr;
+        RV_TRY(run_group(ctx, s, di, dpitch, dfs, dout, dpitch, dfs, g, h, w, p, st, &flags));
+        if (opitch == dpitch)
+            CK(cudaMemcpyAsync(out + (size_t)f0 * opitch * h, dout, dfs * g, cudaMemcpyDeviceToHost, st));
+        else
+            CK(cudaMemcpy2DAsync(out + (size_t)f0 * opitch * h, opitch, dout, dpitch, rowb, (size_t)h * g, cudaMemcpyDeviceToHost, st));
+        if (processed_host) {
+            if (flags) CK(cudaMemcpyAsync(processed_host + f0, flags, (size_t)g * 4, cudaMemcpyDeviceToHost, st));
+            else for (int i = 0; i < g; ++i) processed_host[f0 + i] = 1;
+        }
+    }
+    return RV_OK;
+}
+
+int wait_all(rv_ctx *ctx)
+{
+    for (int i = 0; i < NPIPE; ++i) CK(cudaStreamSynchronize(ctx->pipe[i]));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RV_OK;
+}
+
+// stage-level helper: bring an input to the device if it is on the host
+struct Staged {
+    rv_ctx *ctx;
+    void *dev = nullptr;
+    bool owned = false;
+    ~Staged() { if (owned && dev) cudaFree(dev); }
+};
+
+int stage_in(rv_ctx *ctx, Staged &s, const void *p, size_t bytes, int mem_kind)
+{
+    s.ctx = ctx;
+    if (mem_kind == RV_MEM_DEVICE) { s.dev = const_cast<void *>(p); return RV_OK; }
+    CK(cudaMalloc(&s.dev, std::max<size_t>(bytes, 16)));
+    s.owned = true;
+    CK(cudaMemcpyAsync(s.dev, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return RV_OK;
+}
+
+int stage_out(rv_ctx *ctx, Staged &s, void *p, size_t bytes, int mem_kind)
+{
+    s.ctx = ctx;
+    if (mem_kind == RV_MEM_DEVICE) { s.dev = p; return RV_OK; }
+    CK(cudaMalloc(&s.dev, std::max<size_t>(bytes, 16)));
+    s.owned = true;
+    return RV_OK;
+}
+
+int finish_out(rv_ctx *ctx, Staged &s, void *p, size_t bytes, int mem_kind)
+{
+    if (mem_kind != RV_MEM_DEVICE && p) CK(cudaMemcpyAsync(p, s.dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return RV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rv_version(void) { return "rv_b200 0.1 (sm_100a)"; }
+
+int rv_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int rv_create(int device, rv_ctx **out)
+{
+    if (!out) return RV_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return RV_ERR_NODEV;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return RV_ERR_NODEV;
+    if (prop.major != 10) return RV_ERR_NODEV;              // sm_100a code only; no other backend, no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return RV_ERR_CUDA;
+    rv_ctx *ctx = new (std::nothrow) rv_ctx();
+    if (!ctx) return RV_ERR_NOMEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
+    for (int i = 0; i < NPIPE; ++i)
+        if (cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
+    // LAB tables
+    LabTabs *t = new (std::nothrow) LabTabs();
+    if (!t) { delete ctx; return RV_ERR_NOMEM; }
+    memset(t, 0, sizeof *t);
+    memcpy(t->g8, RV_LAB_G8, sizeof RV_LAB_G8);
+    memcpy(t->yt, RV_LAB_YT, sizeof RV_LAB_YT);
+    memcpy(t->ft, RV_LAB_FT, sizeof RV_LAB_FT);
+    memcpy(t->cb, RV_LAB_CB, sizeof RV_LAB_CB);
+    memcpy(t->ig, RV_LAB_IG, sizeof RV_LAB_IG);
+    cudaError_t e = cudaMemcpyToSymbol(g_lab, t, sizeof *t);
+    delete t;
+    if (e != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
+    *out = ctx;
+    return RV_OK;
+}
+
+void rv_destroy(rv_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    Buf *sets[] = {ctx->hist, ctx->quads, ctx->lut, ctx->flags, ctx->mm, ctx->din, ctx->dout};
+    for (Buf *set : sets)
+        for (int i = 0; i <= NPIPE; ++i)
+            if (set[i].p) cudaFree(set[i].p);
+    if (ctx->scratch.p) cudaFree(ctx->scratch.p);
+    for (const TimedLaunch &t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for (int i = 0; i < NPIPE; ++i)
+        if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *rv_last_error(const rv_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+int rv_set_option(rv_ctx *ctx, const char *name, long value)
+{
+    if (!ctx || !name) return RV_ERR_ARG;
+    if (strcmp(name, "group_frames") == 0) { ctx->group_frames = value; return RV_OK; }
+    if (strcmp(name, "chunk_frames") == 0) { ctx->chunk_frames = value; return RV_OK; }
+    if (strcmp(name, "kernel_timing") == 0) { ctx->kernel_timing = value; return RV_OK; }
+    return fail(ctx, RV_ERR_ARG, "unknown option '%s'", name);
+}
+
+long rv_launch_count(const rv_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int rv_alloc_pinned(rv_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) return RV_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaHostAlloc(out, std::max<size_t>(bytes, 16), cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(ctx, RV_ERR_NOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return RV_OK;
+}
+
+int rv_free_pinned(rv_ctx *ctx, void *p)
+{
+    if (!ctx) return RV_ERR_ARG;
+    if (p) CK(cudaFreeHost(p));
+    return RV_OK;
+}
+
+int rv_alloc_device(rv_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) return RV_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(out, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) return fail(ctx, RV_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return RV_OK;
+}
+
+int rv_free_device(rv_ctx *ctx, void *p)
+{
+    if (!ctx) return RV_ERR_ARG;
+    if (p) CK(cudaFree(p));
+    return RV_OK;
+}
+
+int rv_memcpy(rv_ctx *ctx, void *dst, const void *src, size_t bytes, int kind)
+{
+    if (!ctx) return RV_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpyAsync(dst, src, bytes, k, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RV_OK;
+}
+
+int rv_sync(rv_ctx *ctx)
+{
+    if (!ctx) return RV_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return wait_all(ctx);
+}
+
+int rv_kernel_time(rv_ctx *ctx, int which, double *ms_total, long *launches)
+{
+    if (!ctx || which < 0 || which > 2) return RV_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->timed.empty()) {
+        RV_TRY(wait_all(ctx));
+        for (const TimedLaunch &t : ctx->timed) {
+            float ms = 0.f;
+            CK(cudaEventSynchronize(t.b));
+            CK(cudaEventElapsedTime(&ms, t.a, t.b));
+            ctx->k_ms[t.which] += ms;
+            ctx->k_n[t.which] += 1;
+            ctx->ev_pool.push_back(t.a);
+            ctx->ev_pool.push_back(t.b);
+        }
+        ctx->timed.clear();
+    }
+    if (ms_total) *ms_total = ctx->k_ms[which];
+    if (launches) *launches = ctx->k_n[which];
+    return RV_OK;
+}
+
+int rv_kernel_time_reset(rv_ctx *ctx)
+{
+    if (!ctx) return RV_ERR_ARG;
+    double d; long l;
+    RV_TRY(rv_kernel_time(ctx, 0, &d, &l));
+    for (int i = 0; i < 3; ++i) { ctx->k_ms[i] = 0; ctx->k_n[i] = 0; }
+    return RV_OK;
+}
+
+int rv_submit(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w, size_t in_pitch, size_t out_pitch,
+              const rv_params *p, int mem_kind, void *stream)
+{
+    RV_TRY(check_frames(ctx, in, out, n, h, w, in_pitch, out_pitch));
+    RV_TRY(check_params(ctx, p));
+    if (!p->clahe && p->ksize == 0) return fail(ctx, RV_ERR_ARG, "nothing to do (no CLAHE, no median)");
+    if (n == 0) return RV_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (mem_kind == RV_MEM_DEVICE)
+        return chain_device(ctx, in, out, n, h, w, in_pitch, out_pitch, p, nullptr, stream ? (cudaStream_t)stream : ctx->stream);
+    return chain_host(ctx, in, out, n, h, w, in_pitch, out_pitch, p, nullptr);
+}
+
+int rv_wait(rv_ctx *ctx) { return rv_sync(ctx); }
+
+int rv_chain_u8(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w, size_t in_pitch, size_t out_pitch,
+                const rv_params *p, int mem_kind, int32_t *processed, void *stream)
+{
+    RV_TRY(check_frames(ctx, in, out, n, h, w, in_pitch, out_pitch));
+    RV_TRY(check_params(ctx, p));
+    if (!p->clahe && p->ksize == 0) return fail(ctx, RV_ERR_ARG, "nothing to do (no CLAHE, no median)");
+    if (n == 0) return RV_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (mem_kind == RV_MEM_DEVICE) {
+        cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+        RV_TRY(chain_device(ctx, in, out, n, h, w, in_pitch, out_pitch, p, processed, st));
+        CK(cudaStreamSynchronize(st));
+        return RV_OK;
+    }
+    RV_TRY(chain_host(ctx, in, out, n, h, w, in_pitch, out_pitch, p, processed));
+    return wait_all(ctx);
+}
+
+int rv_luma_hist(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t pitch, int space, int grid, int32_t *hist,
+                 uint8_t *luma, int32_t *gray_minmax, int mem_kind)
+{
+    RV_TRY(check_frames(ctx, in, in, n, h, w, pitch, pitch));
+    if (!hist) return fail(ctx, RV_ERR_ARG, "null hist");
+    if (grid < 1 || grid > 256) return fail(ctx, RV_ERR_ARG, "bad grid %d", grid);
+    if (n == 0) return RV_OK;
+    CK(cudaSetDevice(ctx->device));
+    const Geo g = make_geo(h, w, grid);
+    const size_t hb = (size_t)n * grid * grid * 256 * 4, lb = (size_t)n * h * w, mb = (size_t)n * 8;
+    Staged si, sh, sl, sm;
+    RV_TRY(stage_in(ctx, si, in, pitch * h * n, mem_kind));
+    RV_TRY(stage_out(ctx, sh, hist, hb, mem_kind));
+    if (luma) RV_TRY(stage_out(ctx, sl, luma, lb, mem_kind));
+    if (gray_minmax) RV_TRY(stage_out(ctx, sm, gray_minmax, mb, mem_kind));
+    RV_TRY(launch_hist(ctx, (const uint8_t *)si.dev, pitch, pitch * h, g, space, n, (int32_t *)sh.dev,
+                       luma ? (uint8_t *)sl.dev : nullptr, gray_minmax ? (int32_t *)sm.dev : nullptr, ctx->stream));
+    RV_TRY(finish_out(ctx, sh, hist, hb, mem_kind));
+    if (luma) RV_TRY(finish_out(ctx, sl, luma, lb, mem_kind));
+    if (gray_minmax) RV_TRY(finish_out(ctx, sm, gray_minmax, mb, mem_kind));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RV_OK;
+}
+
+int rv_build_lut(rv_ctx *ctx, const int32_t *hist, int n, int h, int w, int grid, double clip_limit, uint8_t *lut, int mem_kind)
+{
+    if (!ctx) return RV_ERR_ARG;
+    if (!hist || !lut) return fail(ctx, RV_ERR_ARG, "null pointer");
+    if (n < 0 || h < 1 || w < 1 || grid < 1 || grid > 256) return fail(ctx, RV_ERR_ARG, "bad shape");
+    if (n == 0) return RV_OK;
+    CK(cudaSetDevice(ctx->device));
+    const Geo g = make_geo(h, w, grid);
+    const size_t hb = (size_t)n * grid * grid * 256 * 4, lb = (size_t)n * grid * grid * 256;
+    Staged sh, sl;
+    RV_TRY(stage_in(ctx, sh, hist, hb, mem_kind));
+    RV_TRY(stage_out(ctx, sl, lut, lb, mem_kind));
+    RV_TRY(ensure(ctx, ctx->scratch, (size_t)n * (grid + 1) * (grid + 1) * 256 * 4));
+    RV_TRY(launch_lut(ctx, (const int32_t *)sh.dev, g, clip_limit, n, (uint8_t *)sl.dev, (uint32_t *)ctx->scratch.p, ctx->stream));
+    RV_TRY(finish_out(ctx, sl, lut, lb, mem_kind));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RV_OK;
+}
+
+int rv_clahe_dehaze(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w, size_t in_pitch, size_t out_pitch,
+                    int space, double clip_limit, int grid, int mem_kind)
+{
+    rv_params p;
+    memset(&p, 0, sizeof p);
+    p.space = space; p.grid = grid; p.ksize = 0; p.clahe = 1; p.clip_limit = clip_limit;
+    return rv_chain_u8(ctx, in, out, n, h, w, in_pitch, out_pitch, &p, mem_kind, nullptr, nullptr);
+}
+
+int rv_median(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w, size_t in_pitch, size_t out_pitch, int ksize,
+              int mem_kind)
+{
+    rv_params p;
+    memset(&p, 0, sizeof p);
+    p.space = RV_SPACE_YCRCB; p.grid = 2; p.ksize = ksize; p.clahe = 0;
+    if (ksize == 0) return fail(ctx, RV_ERR_ARG, "ksize 0");
+    return rv_chain_u8(ctx, in, out, n, h, w, in_pitch, out_pitch, &p, mem_kind, nullptr, nullptr);
+}
+
+int rv_gray_span(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t pitch, int32_t *span, int mem_kind)
+{
+    RV_TRY(check_frames(ctx, in, in, n, h, w, pitch, pitch));
+    if (!span) return fail(ctx, RV_ERR_ARG, "null span");
+    if (n == 0) return RV_OK;
+    CK(cudaSetDevice(ctx->device));
+    const Geo g = make_geo(h, w, 2);
+    Staged si;
+    RV_TRY(stage_in(ctx, si, in, pitch * h * n, mem_kind));
+    RV_TRY(ensure(ctx, ctx->hist[NPIPE], (size_t)n * 4 * 256 * 4));
+    RV_TRY(ensure(ctx, ctx->mm[NPIPE], (size_t)n * 8));
+    RV_TRY(launch_hist(ctx, (const uint8_t *)si.dev, pitch, pitch * h, g, RV_SPACE_YCRCB, n, (int32_t *)ctx->hist[NPIPE].p, nullptr,
+                       (int32_t *)ctx->mm[NPIPE].p, ctx->stream));
+    int32_t *mm = new (std::nothrow) int32_t[2 * (size_t)n];
+    if (!mm) return fail(ctx, RV_ERR_NOMEM, "host alloc");
+    cudaError_t e = cudaMemcpyAsync(mm, ctx->mm[NPIPE].p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { delete[] mm; return fail(ctx, RV_ERR_CUDA, "gray span: %s", cudaGetErrorString(e)); }
+    if (mem_kind == RV_MEM_DEVICE) {
+        int32_t *tmp = new (std::nothrow) int32_t[n];
+        if (!tmp) { delete[] mm; return fail(ctx, RV_ERR_NOMEM, "host alloc"); }
+        for (int i = 0; i < n; ++i) tmp[i] = mm[2 * i + 1] - mm[2 * i];
+        e = cudaMemcpy(span, tmp, (size_t)n * 4, cudaMemcpyHostToDevice);
+        delete[] tmp;
+    } else {
+        for (int i = 0; i < n; ++i) span[i] = mm[2 * i + 1] - mm[2 * i];
+    }
+    delete[] mm;
+    if (e != cudaSuccess) return fail(ctx, RV_ERR_CUDA, "gray span copy: %s", cudaGetErrorString(e));
+    return RV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,632 @@
+/*
+ * rv_kernels.cuh -- sm_100a kernels of the preprocessing chain (CLAHEDehaze -> MedianDerain).
+ *
+ * Arithmetic follows OpenCV's 8-bit fixed-point paths exactly; the
+ * reference only *calls* them: /root/reference/src/preprocess/ops/clahe_dehaze.py:19-30 and
+ * ops/median_derain.py:14.  Three kernels on the hot path:
+ *
+ *   k_luma_hist   BGR -> luminance (Y of YCrCb / L of LAB) + per-tile 256-bin histograms
+ *                 (per-warp private sub-histograms in shared memory), optional gray min/max
+ *   k_build_lut   clip + redistribute + prefix sum -> u8 LUT per tile (one warp per tile,
+ *                 shuffle scans) and the four-LUT "quad" tables used by the interpolation
+ *   k_chain       per 120x32 output tile: forward colour conversion, bilinear four-LUT blend in
+ *                 float32 without FMA contraction, inverse colour conversion, k x k median from a
+ *                 shared-memory tile (packed u16x2 selection network), coalesced store
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rv_lab_tables.h"
+#include "rv_median_net.h"
+
+namespace rv {
+
+struct Geo {
+    int H, W;          // frame size
+    int grid;          // tiles per side
+    int tw, th;        // tile size of the (REFLECT_101-padded) plane, clahe.cpp semantics (A.3)
+    float inv_tw, inv_th;
+};
+
+// ---------------------------------------------------------------------------------------------
+// LAB tables in global memory (copied into shared memory by the kernels that need them)
+// ---------------------------------------------------------------------------------------------
+struct LabTabs {
+    uint16_t g8[256];
+    uint16_t yt[256];
+    uint16_t ft[256];
+    uint16_t cb[2048];     // entries 0..2040 reachable; [2041..2047] padding
+    uint8_t ig[4096];
+};
+static_assert(sizeof(LabTabs) % 16 == 0, "LabTabs must be 16-byte granular");
+__device__ LabTabs g_lab;   // filled once per context from rv_lab_tables.h
+
+__device__ __forceinline__ int sat8(int v) { return min(max(v, 0), 255); }
+
+// A.1 forward
+__device__ __forceinline__ void ycrcb_fwd(int B, int G, int R, int &Y, int &Cr, int &Cb)
+{
+    Y = (4899 * R + 9617 * G + 1868 * B + 8192) >> 14;
+    Cr = sat8(((R - Y) * 11682 + ((128 << 14) + 8192)) >> 14);
+    Cb = sat8(((B - Y) * 9241 + ((128 << 14) + 8192)) >> 14);
+}
+// A.1 inverse
+__device__ __forceinline__ void ycrcb_inv(int Y, int Cr, int Cb, int &B, int &G, int &R)
+{
+    const int cb = Cb - 128, cr = Cr - 128;
+    B = sat8(Y + ((cb * 29049 + 8192) >> 14));
+    G = sat8(Y + ((cb * -5636 + cr * -11698 + 8192) >> 14));
+    R = sat8(Y + ((cr * 22987 + 8192) >> 14));
+}
+// A.5
+__device__ __forceinline__ int gray_of(int B, int G, int R) { return (3735 * B + 19235 * G + 9798 * R + 16384) >> 15; }
+
+// A.2 forward, luminance only
+__device__ __forceinline__ int lab_L(const LabTabs *t, int B, int G, int R)
+{
+    const int r = t->g8[R], g = t->g8[G], b = t->g8[B];
+    const int fY = t->cb[(871 * r + 2929 * g + 296 * b + 2048) >> 12];
+    return (296 * fY - 1336934 + 16384) >> 15;
+}
+// A.2 forward, all three
+__device__ __forceinline__ void lab_fwd(const LabTabs *t, int B, int G, int R, int &L, int &a, int &bb)
+{
+    const int r = t->g8[R], g = t->g8[G], b = t->g8[B];
+    const int fX = t->cb[(1777 * r + 1541 * g + 778 * b + 2048) >> 12];
+    const int fY = t->cb[(871 * r + 2929 * g + 296 * b + 2048) >> 12];
+    const int fZ = t->cb[(73 * r + 448 * g + 3575 * b + 2048) >> 12];
+    L = (296 * fY - 1336934 + 16384) >> 15;
+    a = sat8((500 * (fX - fY) + ((128 << 15) + 16384)) >> 15);
+    bb = sat8((200 * (fY - fZ) + ((128 << 15) + 16384)) >> 15);
+}
+__device__ __forceinline__ int lab_xz(int i)
+{
+    const int lin = (i * 108) / 841 - 290;            // truncating division, as in C
+    const int cub = (((i * i) >> 14) * i) >> 14;
+    return i <= 3390 ? lin : cub;
+}
+// A.2 inverse
+__device__ __forceinline__ void lab_inv(const LabTabs *t, int L, int a, int b, int &B, int &G, int &R)
+{
+    const int y = t->yt[L], fy = t->ft[L];
+    const int adiv = ((5 * a * 53687 + 128) >> 13) - 4194;
+    const int bdiv = ((b * 41943 + 16) >> 9) - 10485 + 1;
+    const int x = lab_xz(fy + adiv);
+    const int z = lab_xz(fy - bdiv);
+    int ro = (12615 * x - 6296 * y - 2223 * z + 8192) >> 14;
+    int go = (-3773 * x + 7684 * y + 185 * z + 8192) >> 14;
+    int bo = (217 * x - 836 * y + 4715 * z + 8192) >> 14;
+    ro = min(max(ro, 0), 4095);
+    go = min(max(go, 0), 4095);
+    bo = min(max(bo, 0), 4095);
+    B = t->ig[bo];
+    G = t->ig[go];
+    R = t->ig[ro];
+}
+
+__device__ __forceinline__ int reflect101(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+__device__ __forceinline__ void copy_lab_tabs(LabTabs *dst)
+{
+    const uint4 *s = reinterpret_cast<const uint4 *>(&g_lab);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(LabTabs) / 16); i += blockDim.x) d[i] = s[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: luminance + per-tile histograms
+// grid = (slices, tiles, frames), block = 256.  hist must be zeroed; slices accumulate with atomics.
+// ---------------------------------------------------------------------------------------------
+constexpr int HIST_THREADS = 256;
+constexpr int HIST_WARPS = HIST_THREADS / 32;
+
+template <int SPACE>
+__global__ void __launch_bounds__(HIST_THREADS)
+k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g, int rows_per_slice,
+            int32_t *__restrict__ hist, uint8_t *__restrict__ luma, int32_t *__restrict__ gray_minmax)
+{
+    __shared__ uint32_t wh[HIST_WARPS][256];
+    __shared__ __align__(16) unsigned char tab_raw[SPACE == 1 ? sizeof(LabTabs) : 16];
+    LabTabs *tabs = reinterpret_cast<LabTabs *>(tab_raw);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tile = blockIdx.y, f = blockIdx.z;
+    const int ty = tile / g.grid, tx = tile - ty * g.grid;
+    for (int i = tid; i < HIST_WARPS * 256; i += HIST_THREADS) (&wh[0][0])[i] = 0;
+    if (SPACE == 1) copy_lab_tabs(tabs);
+    __syncthreads();
+
+    const uint8_t *frame = src + (size_t)f * fstride;
+    const int x0 = tx * g.tw, y0 = ty * g.th + blockIdx.x * rows_per_slice;
+    const int y1 = min(y0 + rows_per_slice, (ty + 1) * g.th);
+    const int nrows = y1 - y0;
+    uint32_t *myh = wh[warp];
+    int gmin = 255, gmax = 0;
+    const bool want_gray = gray_minmax != nullptr;
+
+    auto one = [&](int B, int G, int R) -> int {
+        int v;
+        if (SPACE == 1) v = lab_L(tabs, B, G, R);
+        else v = (4899 * R + 9617 * G + 1868 * B + 8192) >> 14;
+        atomicAdd(&myh[v], 1u);
+        return v;
+    };
+
+    const bool interior = (x0 + g.tw <= g.W) && (y1 <= g.H);
+    const bool vec_ok = interior && (g.tw % 4 == 0) && (pitch % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(frame) & 3) == 0);
+    if (nrows > 0 && vec_ok) {
+        const int gpr = g.tw >> 2;                 // 4-pixel groups per tile row
+        const int total = nrows * gpr;
+        const float inv_gpr = 1.0f / (float)gpr;
+        for (int idx = tid; idx < total; idx += HIST_THREADS) {
+            int r = __float2int_rz(__int2float_rn(idx) * inv_gpr);
+            int gx = idx - r * gpr;
+            if (gx < 0) { gx += gpr; --r; }
+            if (gx >= gpr) { gx -= gpr; ++r; }
+            const int y = y0 + r, x = x0 + 4 * gx;
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(frame + (size_t)y * pitch + 3 * x);
+            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+            const int B0 = w0 & 255, G0 = (w0 >> 8) & 255, R0 = (w0 >> 16) & 255;
+            const int B1 = w0 >> 24, G1 = w1 & 255, R1 = (w1 >> 8) & 255;
+            const int B2 = (w1 >> 16) & 255, G2 = w1 >> 24, R2 = w2 & 255;
+            const int B3 = (w2 >> 8) & 255, G3 = (w2 >> 16) & 255, R3 = w2 >> 24;
+            const int v0 = one(B0, G0, R0), v1 = one(B1, G1, R1), v2 = one(B2, G2, R2), v3 = one(B3, G3, R3);
+            if (luma) {
+                // x is a multiple of 4 only when tw % 4 == 0 and W*y+x aligned; write bytes to stay general
+                uint8_t *lp = luma + ((size_t)f * g.H + y) * g.W + x;
+                lp[0] = (uint8_t)v0; lp[1] = (uint8_t)v1; lp[2] = (uint8_t)v2; lp[3] = (uint8_t)v3;
+            }
+            if (want_gray) {
+                const int a0 = gray_of(B0, G0, R0), a1 = gray_of(B1, G1, R1), a2 = gray_of(B2, G2, R2), a3 = gray_of(B3, G3, R3);
+                gmin = min(gmin, min(min(a0, a1), min(a2, a3)));
+                gmax = max(gmax, max(max(a0, a1), max(a2, a3)));
+            }
+        }
+    } else if (nrows > 0) {
+        // generic path: ragged tiles (REFLECT_101 padding), odd tile widths, unaligned buffers
+        const int total = nrows * g.tw;
+        for (int idx = tid; idx < total; idx += HIST_THREADS) {
+            const int r = idx / g.tw, cx = idx - r * g.tw;
+            const int ey = y0 + r, ex = x0 + cx;
+            const int y = reflect101(ey, g.H), x = reflect101(ex, g.W);
+            const uint8_t *p = frame + (size_t)y * pitch + 3 * x;
+            const int B = p[0], G = p[1], R = p[2];
+            const int v = one(B, G, R);
+            if (ey < g.H && ex < g.W) {            // each real pixel is visited exactly once un-reflected
+                if (luma) luma[((size_t)f * g.H + y) * g.W + x] = (uint8_t)v;
+                if (want_gray) { const int a = gray_of(B, G, R); gmin = min(gmin, a); gmax = max(gmax, a); }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        uint32_t s = 0;
+#pragma unroll
+        for (int w = 0; w < HIST_WARPS; ++w) s += wh[w][tid];
+        if (s) atomicAdd(&hist[((size_t)f * g.grid * g.grid + tile) * 256 + tid], (int)s);
+    }
+    if (want_gray) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            gmin = min(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+            gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        }
+        if ((tid & 31) == 0 && gmin <= gmax) {
+            atomicMin(&gray_minmax[2 * f], gmin);
+            atomicMax(&gray_minmax[2 * f + 1], gmax);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: LUT + quad tables.  grid = ((grid+1)^2 quads, frames), block = 128 (4 warps = the 4 tiles
+// of the quad; each warp rebuilds its tile's LUT -- 256 bins, 8 per lane, shuffle scans).
+// quad q=(qy,qx): tiles ty in {max(qy-1,0), min(qy,grid-1)}, tx likewise (A.3 tx1/tx2 clamping).
+// quads[f][q][v] = lut[ty1][tx1][v] | lut[ty1][tx2][v]<<8 | lut[ty2][tx1][v]<<16 | lut[ty2][tx2][v]<<24
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_build_lut(const int32_t *__restrict__ hist, int grid, int clip, float lut_scale,
+            uint8_t *__restrict__ lut, uint32_t *__restrict__ quads)
+{
+    __shared__ __align__(16) uint8_t sl[4][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int q = blockIdx.x, f = blockIdx.y;
+    const int nq1 = grid + 1;
+    const int qy = q / nq1, qx = q - qy * nq1;
+    const int ty = (w >> 1) ? min(qy, grid - 1) : max(qy - 1, 0);
+    const int tx = (w & 1) ? min(qx, grid - 1) : max(qx - 1, 0);
+    const size_t tile = (size_t)f * grid * grid + ty * grid + tx;
+
+    int h[8];
+    {
+        const int4 *hp = reinterpret_cast<const int4 *>(hist + tile * 256 + lane * 8);
+        const int4 a = __ldg(hp), b = __ldg(hp + 1);
+        h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
+    }
+    if (clip > 0) {
+        int clipped = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { clipped += max(h[i] - clip, 0); h[i] = min(h[i], clip); }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) clipped += __shfl_xor_sync(0xffffffffu, clipped, o);
+        const int batch = clipped >> 8, residual = clipped & 255;
+        const int step = residual ? max(256 / residual, 1) : 1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int bin = lane * 8 + i;
+            const int qd = bin / step;
+            h[i] += batch + ((residual && bin - qd * step == 0 && qd < residual) ? 1 : 0);
+        }
+    }
+#pragma unroll
+    for (int i = 1; i < 8; ++i) h[i] += h[i - 1];
+    int run = h[7];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, run, o);
+        if (lane >= o) run += t;
+    }
+    const int base = run - h[7];
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float v = __fmul_rn(__int2float_rn(base + h[i]), lut_scale);
+        const uint32_t u = (uint32_t)sat8(__float2int_rn(v));
+        if (i < 4) lo |= u << (8 * i); else hi |= u << (8 * (i - 4));
+    }
+    *reinterpret_cast<uint2 *>(&sl[w][lane * 8]) = make_uint2(lo, hi);
+    if (lut != nullptr && w == 3 && qy < grid && qx < grid)      // warp 3 of quad (ty,tx) owns tile (ty,tx)
+        *reinterpret_cast<uint2 *>(lut + tile * 256 + lane * 8) = make_uint2(lo, hi);
+    __syncthreads();
+    uint32_t *qo = quads + ((size_t)f * nq1 * nq1 + q) * 256;
+    for (int v = threadIdx.x; v < 256; v += 128)
+        qo[v] = (uint32_t)sl[0][v] | ((uint32_t)sl[1][v] << 8) | ((uint32_t)sl[2][v] << 16) | ((uint32_t)sl[3][v] << 24);
+}
+
+// per frame: flag = (max - min < thresh)  (pipeline.py:24-30)
+__global__ void k_gate_flags(const int32_t *__restrict__ gray_minmax, int n, float thresh, int32_t *__restrict__ flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = ((float)(gray_minmax[2 * i + 1] - gray_minmax[2 * i]) < thresh) ? 1 : 0;
+}
+
+__global__ void k_init_minmax(int32_t *mm, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { mm[2 * i] = 255; mm[2 * i + 1] = 0; }
+}
+
+// frames the gate skipped are passed through unchanged
+__global__ void k_gate_copy(const uint8_t *__restrict__ src, size_t spitch, size_t sfstride,
+                            uint8_t *__restrict__ dst, size_t dpitch, size_t dfstride,
+                            int H, int rowbytes, const int32_t *__restrict__ flags)
+{
+    const int f = blockIdx.z;
+    if (flags[f]) return;
+    for (int y = blockIdx.y; y < H; y += gridDim.y) {
+        const uint8_t *s = src + (size_t)f * sfstride + (size_t)y * spitch;
+        uint8_t *d = dst + (size_t)f * dfstride + (size_t)y * dpitch;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowbytes; i += gridDim.x * blockDim.x) d[i] = s[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3+K4: fused apply (+ inverse colour) + median.
+// ---------------------------------------------------------------------------------------------
+constexpr int TILE_W = 120;            // output pixels per tile row
+constexpr int BOX_W = 128;             // staged pixels per row: 4 left + 120 + 4 right
+constexpr int LPAD = 4;
+constexpr int TILE_H = 32;
+constexpr int HALF = TILE_H / 2;       // u16x2 lanes of the median hold rows (s, s + HALF)
+constexpr int CHAIN_THREADS = 256;
+constexpr int CHAIN_WARPS = CHAIN_THREADS / 32;
+constexpr int A_STRIDE = BOX_W * 3;    // bytes per staged BGR row
+constexpr int P_STRIDE = BOX_W;        // words per plane row (one u16x2 word per pixel)
+constexpr int O_STRIDE = TILE_W * 3;   // bytes per output staging row
+constexpr int MAXQ = 6;                // quad tables kept in shared memory per CTA
+
+struct ChainArgs {
+    const uint8_t *src; size_t spitch, sfstride;
+    uint8_t *dst; size_t dpitch, dfstride;
+    Geo g;
+    const uint32_t *quads;             // [frames][(grid+1)^2][256]
+    const int32_t *flags;              // optional per-frame gate flags (0 = skip frame)
+};
+
+template <int K> struct MedianCfg;
+template <> struct MedianCfg<0> { static constexpr int M = 4; };
+template <> struct MedianCfg<3> { static constexpr int M = RV_MEDIAN3_M; };
+template <> struct MedianCfg<5> { static constexpr int M = RV_MEDIAN5_M; };
+template <> struct MedianCfg<7> { static constexpr int M = RV_MEDIAN7_M; };
+template <> struct MedianCfg<9> { static constexpr int M = RV_MEDIAN9_M; };
+
+template <int K, int NC, int M>
+__device__ __forceinline__ void median_net(const uint32_t (&v)[NC][K], uint32_t (&out)[M])
+{
+    if constexpr (K == 3) rv_median3_net(v, out);
+    else if constexpr (K == 5) rv_median5_net(v, out);
+    else if constexpr (K == 7) rv_median7_net(v, out);
+    else rv_median9_net(v, out);
+}
+
+template <int MODE, int K>
+struct ChainSmem {
+    static constexpr int R = K / 2;
+    static constexpr int BOX_H = TILE_H + 2 * R;
+    static constexpr int NSLOT = HALF + 2 * R;
+    static constexpr size_t a_bytes = (size_t)BOX_H * A_STRIDE;
+    static constexpr size_t p_bytes = K > 0 ? (size_t)3 * NSLOT * P_STRIDE * 4 : (size_t)TILE_H * O_STRIDE;  // K==0: output staging
+    static constexpr size_t row_bytes = (size_t)BOX_H * 16;
+    static constexpr size_t q_bytes = MODE == 2 ? 0 : (size_t)MAXQ * 256 * 4;
+    static constexpr size_t t_bytes = MODE == 1 ? sizeof(LabTabs) : 0;
+    static constexpr size_t off_a = 0;
+    static constexpr size_t off_p = (a_bytes + 15) & ~(size_t)15;
+    static constexpr size_t off_row = off_p + ((p_bytes + 15) & ~(size_t)15);
+    static constexpr size_t off_q = off_row + row_bytes;
+    static constexpr size_t off_t = off_q + q_bytes;
+    static constexpr size_t total = off_t + t_bytes;
+};
+
+// MODE: 0 = CLAHE in YCrCb, 1 = CLAHE in LAB, 2 = no CLAHE (median only).  K: 0 (no median), 3, 5, 7, 9.
+template <int MODE, int K>
+__global__ void __launch_bounds__(CHAIN_THREADS)
+k_chain(const ChainArgs a)
+{
+    using S = ChainSmem<MODE, K>;
+    constexpr int R = S::R, BOX_H = S::BOX_H;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint8_t *A = smem + S::off_a;
+    uint32_t *P = reinterpret_cast<uint32_t *>(smem + S::off_p);
+    float4 *rowp = reinterpret_cast<float4 *>(smem + S::off_row);
+    uint32_t *Qs = reinterpret_cast<uint32_t *>(smem + S::off_q);
+    const LabTabs *tabs = reinterpret_cast<const LabTabs *>(smem + S::off_t);
+    uint8_t *O = K > 0 ? A : reinterpret_cast<uint8_t *>(P);       // output staging
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.z;
+    if (a.flags != nullptr && a.flags[f] == 0) return;            // gated-off frame: k_gate_copy handles it
+    const Geo g = a.g;
+    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    const uint8_t *frame = a.src + (size_t)f * a.sfstride;
+
+    // ---- phase 0: stage the BGR box (rows clamped = BORDER_REPLICATE of the later median), tables
+    {
+        const long bx0 = 3L * (x0 - LPAD);                        // first byte of the box in the row (may be < 0)
+        const int rowbytes = 3 * g.W;
+        const bool al4 = ((reinterpret_cast<uintptr_t>(frame) & 3) == 0) && (a.spitch % 4 == 0);
+        for (int i = tid; i < BOX_H * (A_STRIDE / 4); i += CHAIN_THREADS) {
+            const int ry = i / (A_STRIDE / 4), wx = i - ry * (A_STRIDE / 4);
+            const int gy = min(max(y0 - R + ry, 0), g.H - 1);
+            const long b = bx0 + 4L * wx;
+            const uint8_t *rp = frame + (size_t)gy * a.spitch;
+            uint32_t v = 0;
+            if (al4 && b >= 0 && b + 4 <= rowbytes) {
+                v = __ldg(reinterpret_cast<const uint32_t *>(rp + b));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (b + k >= 0 && b + k < rowbytes) v |= (uint32_t)rp[b + k] << (8 * k);
+            }
+            reinterpret_cast<uint32_t *>(A)[i] = v;
+        }
+    }
+    // interpolation terms of this lane's four pixels (A.3), evaluated at the clamped coordinate
+    float xa[4], xa1[4], cxa[4], cxa1[4];
+    int qxl[4];
+    int qx_lo = 0, nqx = 1, qy_lo = 0;
+    bool q_smem = true;
+    const bool lane_inside = (x0 - LPAD + 4 * lane >= 0) && (x0 - LPAD + 4 * lane + 3 < g.W);
+    if (MODE != 2) {
+        auto qof = [](int p, float inv) { return (int)floorf(__fsub_rn(__fmul_rn((float)p, inv), 0.5f)) + 1; };
+        const int cx_first = min(max(x0 - LPAD, 0), g.W - 1), cx_last = min(max(x0 - LPAD + BOX_W - 1, 0), g.W - 1);
+        const int cy_first = min(max(y0 - R, 0), g.H - 1), cy_last = min(max(y0 - R + BOX_H - 1, 0), g.H - 1);
+        qx_lo = qof(cx_first, g.inv_tw);
+        qy_lo = qof(cy_first, g.inv_th);
+        nqx = qof(cx_last, g.inv_tw) - qx_lo + 1;
+        const int nqy = qof(cy_last, g.inv_th) - qy_lo + 1;
+        const int nq = nqx * nqy;
+        q_smem = nq <= MAXQ;
+        const uint32_t *qf = a.quads + (size_t)f * (g.grid + 1) * (g.grid + 1) * 256;
+        if (q_smem) {
+            for (int i = tid; i < nq * 256; i += CHAIN_THREADS) {
+                const int lq = i >> 8, v = i & 255;
+                const int qy = qy_lo + lq / nqx, qx = qx_lo + lq % nqx;
+                Qs[i] = __ldg(qf + ((size_t)qy * (g.grid + 1) + qx) * 256 + v);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cx = min(max(x0 - LPAD + 4 * lane + j, 0), g.W - 1);
+            const float txf = __fsub_rn(__fmul_rn((float)cx, g.inv_tw), 0.5f);
+            const float fl = floorf(txf);
+            xa[j] = __fsub_rn(txf, fl);
+            xa1[j] = __fsub_rn(1.0f, xa[j]);
+            cxa[j] = -8388608.0f * xa[j];        // exact (power-of-two scale)
+            cxa1[j] = -8388608.0f * xa1[j];
+            qxl[j] = (int)fl + 1 - qx_lo;
+        }
+        for (int ry = tid; ry < BOX_H; ry += CHAIN_THREADS) {
+            const int gy = min(max(y0 - R + ry, 0), g.H - 1);
+            const float tyf = __fsub_rn(__fmul_rn((float)gy, g.inv_th), 0.5f);
+            const float fl = floorf(tyf);
+            const float ya = __fsub_rn(tyf, fl);
+            const int qy = (int)fl + 1;
+            rowp[ry] = make_float4(ya, __fsub_rn(1.0f, ya), __int_as_float(q_smem ? (qy - qy_lo) : qy), 0.f);
+        }
+        if (MODE == 1) copy_lab_tabs(const_cast<LabTabs *>(tabs));
+    }
+    __syncthreads();
+
+    // ---- phase 1: CLAHE on the luminance of every staged pixel (or plain unpack when MODE == 2)
+    const uint32_t *qglob = (MODE != 2) ? a.quads + (size_t)f * (g.grid + 1) * (g.grid + 1) * 256 : nullptr;
+    auto compute_row = [&](int ry, int (&o)[12]) {
+        int Bv[4], Gv[4], Rv[4];
+        const uint8_t *ar = A + ry * A_STRIDE;
+        if (lane_inside) {
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(ar + 12 * lane);
+            const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
+            Bv[0] = w0 & 255; Gv[0] = (w0 >> 8) & 255; Rv[0] = (w0 >> 16) & 255;
+            Bv[1] = w0 >> 24; Gv[1] = w1 & 255; Rv[1] = (w1 >> 8) & 255;
+            Bv[2] = (w1 >> 16) & 255; Gv[2] = w1 >> 24; Rv[2] = w2 & 255;
+            Bv[3] = (w2 >> 8) & 255; Gv[3] = (w2 >> 16) & 255; Rv[3] = w2 >> 24;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int cx = min(max(x0 - LPAD + 4 * lane + j, 0), g.W - 1);
+                const uint8_t *p = ar + 3 * (cx - (x0 - LPAD));
+                Bv[j] = p[0]; Gv[j] = p[1]; Rv[j] = p[2];
+            }
+        }
+        if (MODE == 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { o[j] = Bv[j]; o[4 + j] = Gv[j]; o[8 + j] = Rv[j]; }
+            return;
+        }
+        const float4 rp = rowp[ry];
+        const float ya = rp.x, ya1 = rp.y;
+        const int qyl = __float_as_int(rp.z);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int L, c1, c2;
+            if (MODE == 1) lab_fwd(tabs, Bv[j], Gv[j], Rv[j], L, c1, c2);
+            else ycrcb_fwd(Bv[j], Gv[j], Rv[j], L, c1, c2);
+            uint32_t q;
+            if (q_smem) q = Qs[((qyl * nqx + qxl[j]) << 8) + L];
+            else q = __ldg(qglob + (((size_t)qyl * (g.grid + 1) + (qxl[j] + qx_lo)) << 8) + L);
+            // 0x4B0000vv = 2^23 + vv ; fma(2^23 + v, w, -2^23 * w) == v * w rounded once (A.3: no FMA contraction
+            // between the products and the sums -- each step below is individually rounded)
+            const float m00 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7440));
+            const float m01 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7441));
+            const float m10 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7442));
+            const float m11 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7443));
+            const float p00 = __fmaf_rn(m00, xa1[j], cxa1[j]);
+            const float p01 = __fmaf_rn(m01, xa[j], cxa[j]);
+            const float p10 = __fmaf_rn(m10, xa1[j], cxa1[j]);
+            const float p11 = __fmaf_rn(m11, xa[j], cxa[j]);
+            const float top = __fmul_rn(__fadd_rn(p00, p01), ya1);
+            const float bot = __fmul_rn(__fadd_rn(p10, p11), ya);
+            const float res = __fadd_rn(top, bot);
+            const int L2 = min(__float_as_int(__fadd_rn(res, 12582912.0f)) & 0x3FF, 255);   // round-half-even, saturate
+            if (MODE == 1) lab_inv(tabs, L2, c1, c2, o[j], o[4 + j], o[8 + j]);
+            else ycrcb_inv(L2, c1, c2, o[j], o[4 + j], o[8 + j]);
+        }
+    };
+
+    if constexpr (K == 0) {
+        // no median: write the interleaved result straight to the staging tile (lanes 0 and 31 hold halo only)
+        for (int ry = warp; ry < TILE_H; ry += CHAIN_WARPS) {
+            if (y0 + ry >= g.H) break;
+            if (lane >= 1 && lane <= 30) {
+                int o[12];
+                compute_row(ry, o);
+                uint32_t *op = reinterpret_cast<uint32_t *>(O + ry * O_STRIDE + 12 * (lane - 1));
+                op[0] = (uint32_t)o[0] | ((uint32_t)o[4] << 8) | ((uint32_t)o[8] << 16) | ((uint32_t)o[1] << 24);
+                op[1] = (uint32_t)o[5] | ((uint32_t)o[9] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[6] << 24);
+                op[2] = (uint32_t)o[10] | ((uint32_t)o[3] << 8) | ((uint32_t)o[7] << 16) | ((uint32_t)o[11] << 24);
+            }
+        }
+    } else {
+        // planes P[c][slot][px]: low half = row `slot`, high half = row `slot + HALF` of the box
+        constexpr int NSLOT = S::NSLOT;
+        for (int s = warp; s < HALF; s += CHAIN_WARPS) {
+            int o0[12], o1[12];
+            compute_row(s, o0);
+            compute_row(s + HALF, o1);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint4 w;
+                w.x = (uint32_t)o0[4 * c + 0] | ((uint32_t)o1[4 * c + 0] << 16);
+                w.y = (uint32_t)o0[4 * c + 1] | ((uint32_t)o1[4 * c + 1] << 16);
+                w.z = (uint32_t)o0[4 * c + 2] | ((uint32_t)o1[4 * c + 2] << 16);
+                w.w = (uint32_t)o0[4 * c + 3] | ((uint32_t)o1[4 * c + 3] << 16);
+                *reinterpret_cast<uint4 *>(P + ((size_t)c * NSLOT + s) * P_STRIDE + 4 * lane) = w;
+            }
+            if (s < 2 * R) {       // rows [HALF, HALF+2R) are also the low half of slots [HALF, HALF+2R)
+                compute_row(s + TILE_H, o0);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    uint4 w;
+                    w.x = (uint32_t)o1[4 * c + 0] | ((uint32_t)o0[4 * c + 0] << 16);
+                    w.y = (uint32_t)o1[4 * c + 1] | ((uint32_t)o0[4 * c + 1] << 16);
+                    w.z = (uint32_t)o1[4 * c + 2] | ((uint32_t)o0[4 * c + 2] << 16);
+                    w.w = (uint32_t)o1[4 * c + 3] | ((uint32_t)o0[4 * c + 3] << 16);
+                    *reinterpret_cast<uint4 *>(P + ((size_t)c * NSLOT + s + HALF) * P_STRIDE + 4 * lane) = w;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: k x k median per channel plane; lanes of each u16x2 are output rows (s, s+HALF)
+    if constexpr (K > 0) {
+        constexpr int NSLOT = S::NSLOT;
+        constexpr int M = MedianCfg<K>::M;
+        constexpr int NG = TILE_W / M;               // output groups per row
+        constexpr int NC = M + K - 1;                // pixel columns per group
+        for (int task = tid; task < 3 * NG * HALF; task += CHAIN_THREADS) {
+            const int m = task % NG;
+            const int t2 = task / NG;
+            const int c = t2 % 3, s = t2 / 3;
+            if (x0 + M * m >= g.W) continue;
+            if (y0 + s >= g.H) continue;
+            uint32_t v[NC][K];
+            const uint32_t *pc = P + ((size_t)c * NSLOT + s) * P_STRIDE;
+            if (M == 4) {
+#pragma unroll
+                for (int d = 0; d < K; ++d) {
+                    const uint4 *p4 = reinterpret_cast<const uint4 *>(pc + d * P_STRIDE + 4 * m);
+                    const uint4 q0 = p4[0], q1 = p4[1], q2 = p4[2];
+                    const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[LPAD - R + cc];
+                }
+            } else {
+#pragma unroll
+                for (int d = 0; d < K; ++d)
+#pragma unroll
+                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = pc[d * P_STRIDE + LPAD + M * m - R + cc];
+            }
+            uint32_t out[M];
+            median_net<K, NC, M>(v, out);
+            uint8_t *o0 = O + s * O_STRIDE + 3 * M * m + c;
+            uint8_t *o1 = o0 + HALF * O_STRIDE;
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                o0[3 * j] = (uint8_t)(out[j] & 255);
+                o1[3 * j] = (uint8_t)(out[j] >> 16);
+            }
+        }
+        __syncthreads();
+    } else {
+        __syncthreads();
+    }
+
+    // ---- phase 3: coalesced store of the staging tile
+    {
+        uint8_t *dframe = a.dst + (size_t)f * a.dfstride;
+        const int nb = min(3 * TILE_W, 3 * (g.W - x0));          // valid bytes per row
+        const bool al4 = ((reinterpret_cast<uintptr_t>(dframe) & 3) == 0) && (a.dpitch % 4 == 0);
+        const int rows = min(TILE_H, g.H - y0);
+        for (int i = tid; i < rows * (O_STRIDE / 4); i += CHAIN_THREADS) {
+            const int ry = i / (O_STRIDE / 4), wx = i - ry * (O_STRIDE / 4);
+            const int b = 4 * wx;
+            if (b >= nb) continue;
+            uint8_t *dp = dframe + (size_t)(y0 + ry) * a.dpitch + 3 * (size_t)x0 + b;
+            const uint32_t v = *reinterpret_cast<const uint32_t *>(O + ry * O_STRIDE + b);
+            if (al4 && b + 4 <= nb) {
+                *reinterpret_cast<uint32_t *>(dp) = v;
+            } else {
+                for (int k = 0; k < 4 && b + k < nb; ++k) dp[k] = (uint8_t)(v >> (8 * k));
+            }
+        }
+    }
+}
+
+}  // namespace rv

@@ -1,0 +1,127 @@
+"""PreprocessPipeline -- drop-in for /root/reference/src/preprocess/pipeline.py:7-45.
+
+Same constructor (`enabled`, `chain`, `auto_gate`), same `pipeline(image, ts=None)` call.
+Differences are internal: an adjacent CLAHEDehaze -> MedianDerain pair is dispatched as ONE
+fused GPU pass (the ops stay individually callable), and `process_batch` is the new
+multi-frame entry (no reference counterpart; the reference loop keeps one frame in flight,
+main_preview.py:88-142).
+"""
+from typing import Any, Dict
+
+import numpy as np
+
+from .._native import Params, default_context
+from .base import as_bgr_u8
+from .ops import CLAHEDehaze, MedianDerain
+from .ops import clahe_dehaze as _clahe
+from .ops import median_derain as _median
+from .registry import get_op_class
+
+
+class PreprocessPipeline:
+    def __init__(self, config: Dict[str, Any]):
+        self.enabled = bool(config.get("enabled", True))
+        self.chain_cfg = config.get("chain", []) or []
+        self.auto_gate_cfg = config.get("auto_gate", {}) or {}
+        self.device = config.get("device")          # optional new key; the stock YAML does not set it
+        self.ops = []
+        for node in self.chain_cfg:
+            name = node.get("name")
+            params = node.get("params", {})
+            cls = get_op_class(name)
+            self.ops.append(cls(**params))
+
+    # -- helpers -------------------------------------------------------------------------
+    def _ctx(self):
+        return default_context(self.device)
+
+    def _gate(self):
+        enable = bool(self.auto_gate_cfg.get("enable_low_contrast_gate", False))
+        return enable, float(self.auto_gate_cfg.get("contrast_thresh", 20.0))
+
+    def _low_contrast(self, image) -> bool:
+        """pipeline.py:24-30: gray span < thresh (gray = cv2 BGR2GRAY fixed point, computed on the GPU)."""
+        span = int(self._ctx().gray_span(as_bgr_u8(image)[None])[0])
+        return span < self._gate()[1]
+
+    def _segments(self):
+        """Fold the op list into fused GPU passes: [(Params | op)]; params are re-read every call."""
+        segs, i = [], 0
+        while i < len(self.ops):
+            op = self.ops[i]
+            nxt = self.ops[i + 1] if i + 1 < len(self.ops) else None
+            if type(op).__call__ is CLAHEDehaze.__call__ and nxt is not None and type(nxt).__call__ is MedianDerain.__call__:
+                space, clip, grid = _clahe.coerce(op.params)
+                segs.append(Params.make(space, clip, grid, _median.coerce(nxt.params), clahe=True))
+                i += 2
+            elif type(op).__call__ is CLAHEDehaze.__call__:
+                space, clip, grid = _clahe.coerce(op.params)
+                segs.append(Params.make(space, clip, grid, 0, clahe=True))
+                i += 1
+            elif type(op).__call__ is MedianDerain.__call__:
+                segs.append(Params.make(ksize=_median.coerce(op.params), clahe=False))
+                i += 1
+            else:
+                segs.append(op)         # foreign operator: called as in the reference
+                i += 1
+        return segs
+
+    # -- per-frame contract --------------------------------------------------------------
+    def __call__(self, image: np.ndarray, ts: float = None) -> np.ndarray:
+        if not self.enabled or not self.ops:
+            return image
+        if self._gate()[0]:
+            if not self._low_contrast(image):
+                return image
+        out = image
+        for seg in self._segments():
+            if isinstance(seg, Params):
+                out = self._ctx().chain(as_bgr_u8(out)[None], seg)[0]
+            else:
+                out = seg(out)
+        return out
+
+    # -- new: batched multi-frame entry --------------------------------------------------
+    def process_batch(self, frames: np.ndarray, out: np.ndarray = None) -> np.ndarray:
+        """(B,H,W,3) uint8 -> (B,H,W,3) uint8; equals B per-frame calls bit for bit.
+
+        `frames` / `out` may be pinned arrays from `Context.pinned_empty` (fastest: H2D, kernels
+        and D2H of consecutive chunks overlap).  Frames the low-contrast gate skips are copied
+        through unchanged.
+        """
+        if not isinstance(frames, np.ndarray) or frames.ndim != 4 or frames.shape[3] != 3 or frames.dtype != np.uint8:
+            raise ValueError("frames must be a (B,H,W,3) uint8 numpy array")
+        if not self.enabled or not self.ops:
+            if out is None:
+                return frames
+            np.copyto(out, frames)
+            return out
+        ctx = self._ctx()
+        gate, thresh = self._gate()
+        cur = frames
+        segs = self._segments()
+        if gate and not (len(segs) == 1 and isinstance(segs[0], Params)):
+            # general case: decide per frame up front, run the chain on the selected frames only
+            span = ctx.gray_span(np.ascontiguousarray(frames))
+            sel = np.flatnonzero(span < thresh)
+            res = np.array(frames, copy=True) if out is None else out
+            if out is not None:
+                np.copyto(out, frames)
+            if len(sel):
+                sub = np.ascontiguousarray(frames[sel])
+                for seg in segs:
+                    sub = ctx.chain(sub, seg) if isinstance(seg, Params) else np.stack([seg(f) for f in sub])
+                res[sel] = sub
+            return res
+        for idx, seg in enumerate(segs):
+            last = idx == len(segs) - 1
+            if isinstance(seg, Params):
+                if gate:
+                    seg.gate_enable, seg.gate_thresh = 1, thresh
+                cur = ctx.chain(cur, seg, out=out if last else None)
+            else:
+                cur = np.stack([seg(f) for f in cur])
+                if last and out is not None:
+                    np.copyto(out, cur)
+                    cur = out
+        return cur

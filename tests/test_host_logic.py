@@ -1,0 +1,134 @@
+"""CPU-only checks of the host side: C-ABI surface, plugin contract, batch feeder, sharding."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import rvb200
+    from rvb200 import _native
+    so = rvb200.build_library()
+    assert os.path.exists(so)
+    header = open(os.path.join(ROOT, "include", "rv_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(rv_[a-z0-9_]+)\s*\(", body))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(so)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/rv_b200.h but not exported"
+    assert declared == set(_native.EXPORTS), "ctypes table and header disagree"
+    assert b"sm_100a" in _native.load_library().rv_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import rvb200
+    from rvb200 import _native
+    if _native.load_library().rv_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(rvb200.RvError):
+        rvb200.Context(0)
+    op = rvb200.CLAHEDehaze(space="LAB")
+    with pytest.raises(rvb200.RvError):
+        op(np.zeros((8, 8, 3), np.uint8))
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "road-vision-system_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")) and f != "rv_lab_tables.h":
+                text = open(os.path.join(dirpath, f)).read()
+                assert "rv_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+                assert "import cv2" not in text or f == "capture.py", f
+
+
+def test_pipeline_identity_and_construction():
+    import rvb200
+    img = np.zeros((4, 4, 3), np.uint8)
+    assert rvb200.PreprocessPipeline({"enabled": False, "chain": [{"name": "MedianDerain"}]})(img) is img
+    assert rvb200.PreprocessPipeline({"chain": []})(img, ts=1.0) is img
+    assert rvb200.PreprocessPipeline({"chain": None})(img) is img
+    with pytest.raises(KeyError):
+        rvb200.PreprocessPipeline({"chain": [{"name": "Missing"}]})
+    p = rvb200.PreprocessPipeline({"chain": [{"name": "CUDACLAHEDehaze", "params": {"space": "Lab", "tile_grid": 1, "junk": 3}},
+                                             {"name": "CUDAMedianDerain", "params": {"ksize": 6}}]})
+    segs = p._segments()
+    assert len(segs) == 1 and segs[0].space == 1 and segs[0].grid == 2 and segs[0].ksize == 7 and segs[0].clahe == 1
+    p.ops[1].params["ksize"] = 11               # params are re-read on every call, like the reference
+    assert p._segments()[0].ksize == 9
+    q = rvb200.PreprocessPipeline({"chain": [{"name": "MedianDerain"}, {"name": "CLAHEDehaze"}]})
+    s = q._segments()
+    assert [x.clahe for x in s] == [0, 1] and [x.ksize for x in s] == [3, 0] and s[1].space == 0 and s[1].grid == 8
+
+
+def test_input_validation():
+    from rvb200.preprocess.base import as_bgr_u8
+    with pytest.raises(TypeError):
+        as_bgr_u8([[1, 2, 3]])
+    for bad in [np.zeros((4, 4), np.uint8), np.zeros((4, 4, 4), np.uint8), np.zeros((0, 4, 3), np.uint8)]:
+        with pytest.raises(ValueError):
+            as_bgr_u8(bad)
+    with pytest.raises(ValueError):
+        as_bgr_u8(np.zeros((4, 4, 3), np.float32))
+    base = np.arange(6 * 8 * 3, dtype=np.uint8).reshape(6, 8, 3)
+    for view in [base[::2], base[:, ::2], np.asfortranarray(base)]:
+        c = as_bgr_u8(view)
+        assert c.flags.c_contiguous and np.array_equal(c, view)
+
+
+def test_video_source_read_and_read_batch():
+    import rvb200
+    from rvb200.io_video.capture import SyntheticReader
+    pool = [np.full((6, 8, 3), i, np.uint8) for i in range(3)]
+    vs = rvb200.VideoSource(reader=SyntheticReader(pool, limit=5))
+    fr = vs.read()
+    assert fr.ok and fr.image is pool[0] and isinstance(fr.ts, float)
+    buf = np.empty((8, 6, 8, 3), np.uint8)
+    count, frames, ts = vs.read_batch(8, out=buf)
+    assert count == 4 and frames.shape == (4, 6, 8, 3) and len(ts) == 4 and np.all(np.diff(ts) >= 0)
+    assert [int(f[0, 0, 0]) for f in frames] == [1, 2, 0, 1]
+    assert vs.read().ok is False
+    m = rvb200.FPSMeter(alpha=0.5)
+    m.tick(1.0); m.tick(1.5)
+    assert abs(m.fps - 1.0) < 1e-9
+
+
+def test_median_networks_are_current():
+    """The committed rv_median_net.h is what tools/gen_median_net.py generates (networks verified there)."""
+    path = os.path.join(ROOT, "road-vision-system_b200", "csrc", "rv_median_net.h")
+    before = open(path).read()
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_median_net.py"), "--quick"],
+                          stdout=subprocess.DEVNULL, timeout=600)
+    assert open(path).read() == before
+
+
+def test_shard_plan_and_gloo_world2(tmp_path):
+    """bench.py's sharding helper: frames partition across ranks with no overlap; run it under gloo, world_size 2."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for n, world in [(64, 1), (64, 2), (64, 8), (10, 4), (3, 8)]:
+        parts = [bench.shard_range(n, r, world) for r in range(world)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        assert max(b - a for a, b in parts) - min(b - a for a, b in parts) <= 1
+    script = tmp_path / "w2.py"
+    script.write_text(
+        "import sys; sys.path.insert(0, %r)\n"
+        "import torch, torch.distributed as dist, bench\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "a, b = bench.shard_range(64, r, w)\n"
+        "t = bench.max_over_ranks(float(10 + r), use_cuda=False)\n"
+        "tot = bench.sum_over_ranks(float(b - a), use_cuda=False)\n"
+        "assert t == 11.0 and tot == 64.0, (t, tot)\n"
+        "dist.destroy_process_group()\n" % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                           "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)], env=env, timeout=300)

@@ -1,0 +1,129 @@
+"""Pin the CPU oracle (oracle/rv_oracle.c) against the live OpenCV and the reference-made fixtures.
+
+The arithmetic of the path lives in OpenCV (the reference only calls it:
+/root/reference/src/preprocess/ops/clahe_dehaze.py:19-30, ops/median_derain.py:14), so the
+ground truth is cv2 itself plus tests/golden/ (outputs of the reference's own classes).
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import load_golden_cases, load_sha_pins
+from oracle import rv_oracle as O
+
+cv2 = pytest.importorskip("cv2")
+from oracle import cv2_chain as R  # noqa: E402
+
+
+def all_colours():
+    """Every 24-bit colour once, as a 4096 x 4096 BGR image."""
+    v = np.arange(1 << 24, dtype=np.uint32)
+    img = np.empty((1 << 24, 3), np.uint8)
+    img[:, 0] = v & 255
+    img[:, 1] = (v >> 8) & 255
+    img[:, 2] = v >> 16
+    return img.reshape(4096, 4096, 3)
+
+
+@pytest.mark.parametrize("name,code", [("bgr2ycrcb", "COLOR_BGR2YCrCb"), ("ycrcb2bgr", "COLOR_YCrCb2BGR"),
+                                       ("bgr2lab", "COLOR_BGR2LAB"), ("lab2bgr", "COLOR_LAB2BGR")])
+def test_colour_exhaustive(name, code):
+    img = all_colours()
+    want = cv2.cvtColor(img, getattr(cv2, code))
+    got = getattr(O, name)(img)
+    assert np.array_equal(got, want)
+
+
+def test_gray_exhaustive():
+    img = all_colours()
+    assert np.array_equal(O.bgr2gray(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+
+
+def _planes():
+    rng = np.random.RandomState(7)
+    yield "uniform", rng.randint(0, 256, (270, 480)).astype(np.uint8)
+    yield "foggy", np.clip(rng.normal(185, 12, (216, 384)), 0, 255).astype(np.uint8)
+    yy, xx = np.mgrid[0:200, 0:300]
+    yield "gradient", ((yy + xx) % 256).astype(np.uint8)
+    yield "constant", np.full((96, 128), 200, np.uint8)
+    yield "ragged", rng.randint(0, 256, (123, 457)).astype(np.uint8)
+    yield "one_div", rng.randint(0, 256, (135, 243)).astype(np.uint8)      # H divisible by 9/5/3, W not by 8
+    yield "small", rng.randint(0, 256, (16, 16)).astype(np.uint8)
+    yield "thin", rng.randint(0, 256, (5, 300)).astype(np.uint8)
+
+
+@pytest.mark.parametrize("grid", [2, 7, 8, 16])
+@pytest.mark.parametrize("clip", [0.0, 0.001, 2.0, 3.7, 40.0])
+def test_clahe_plane_matrix(grid, clip):
+    for name, pl in _planes():
+        want = cv2.createCLAHE(clipLimit=clip, tileGridSize=(grid, grid)).apply(pl)
+        got = O.clahe_plane(pl, clip, grid)
+        assert np.array_equal(got, want), (name, grid, clip)
+
+
+def test_clahe_intermediates_hist_and_lut():
+    rng = np.random.RandomState(3)
+    pl = np.clip(rng.normal(150, 30, (240, 320)), 0, 255).astype(np.uint8)
+    grid, clip = 8, 2.0
+    tw, th = O.clahe_geometry(240, 320, grid)
+    assert (tw, th) == (40, 30)
+    hist = O.clahe_hist(pl, grid)
+    lut = O.clahe_lut(hist, 240, 320, grid, clip)
+    for ty in range(grid):
+        for tx in range(grid):
+            crop = np.ascontiguousarray(pl[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw])
+            assert np.array_equal(hist[ty * grid + tx], np.bincount(crop.ravel(), minlength=256))
+            # a 1x1 CLAHE on the crop applies exactly this tile's LUT to every present grey level
+            want = cv2.createCLAHE(clipLimit=clip, tileGridSize=(1, 1)).apply(crop)
+            assert np.array_equal(lut[ty * grid + tx][crop], want)
+
+
+def test_geometry_quirk_both_dims_padded():
+    # A.3: if either dimension is ragged BOTH get padded, a divisible one by a full `grid`
+    assert O.clahe_geometry(1080, 1923, 8) == (241, 136)
+    assert O.clahe_geometry(1080, 1920, 8) == (240, 135)
+    assert O.clahe_geometry(123, 457, 8) == (58, 16)
+
+
+@pytest.mark.parametrize("k", [3, 5, 7, 9])
+def test_median(k):
+    rng = np.random.RandomState(k)
+    for shape in [(64, 80, 3), (7, 5, 3), (1, 9, 3), (33, 1, 3), (40, 41)]:
+        img = rng.randint(0, 256, shape).astype(np.uint8)
+        assert np.array_equal(O.median(img, k), cv2.medianBlur(img, k)), (k, shape)
+    img = (rng.randint(0, 4, (50, 60, 3)) * 60).astype(np.uint8)        # heavy ties
+    assert np.array_equal(O.median(img, k), cv2.medianBlur(img, k))
+
+
+def test_chain_vs_cv2_chain():
+    rng = np.random.RandomState(11)
+    img = rng.randint(0, 256, (180, 320, 3)).astype(np.uint8)
+    for space, grid, k in [("YCrCb", 8, 3), ("LAB", 8, 5), ("LAB", 7, 7), ("YCrCb", 16, 9), ("LAB", 2, 0)]:
+        want = R.chain(img, space, 2.0, grid, k)
+        got = O.chain(img, O.SPACE_LAB if space == "LAB" else O.SPACE_YCRCB, 2.0, grid, k)
+        assert np.array_equal(got, want), (space, grid, k)
+
+
+def test_golden_cases_oracle_and_cv2_chain():
+    cases, gate, _ = load_golden_cases()
+    assert len(cases) >= 10
+    for c in cases:
+        got = O.chain(c["inp"], O.SPACE_LAB if c["space"] == "LAB" else O.SPACE_YCRCB, c["clip"], c["grid"], c["k"])
+        assert np.array_equal(got, c["out"]), c["idx"]
+        assert np.array_equal(R.chain(c["inp"], c["space"], c["clip"], c["grid"], c["k"]), c["out"]), c["idx"]
+
+
+def test_golden_gate():
+    _, gate, z = load_golden_cases()
+    for name, processed in gate:
+        assert (O.gray_span(z[f"in_{name}"]) < 20.0) == bool(int(processed))
+        assert R.low_contrast(z[f"in_{name}"], 20.0) == bool(int(processed))
+
+
+def test_sha_pins_full_size():
+    """Reference PreprocessPipeline outputs at benchmark shapes (SHA-1 recorded by make_golden.py)."""
+    for p in load_sha_pins()[:4]:
+        img = np.random.RandomState(p["seed"]).randint(0, 256, (p["h"], p["w"], 3)).astype(np.uint8)
+        got = O.chain(img, O.SPACE_LAB if p["space"] == "LAB" else O.SPACE_YCRCB, 2.0, p["grid"], p["k"])
+        assert hashlib.sha1(got.tobytes()).hexdigest() == p["sha"], p

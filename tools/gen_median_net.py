@@ -1,0 +1,364 @@
+#!/usr/bin/env python3
+"""Generate the min/max selection networks used by the CUDA median kernel.
+
+The k x k median of /root/reference/src/preprocess/ops/median_derain.py:14 (cv2.medianBlur)
+is computed per byte lane with packed 16-bit min/max (VIMNMX.U16x2 on sm_100a).  One call of
+the generated function produces M horizontally adjacent outputs of one channel plane from
+(M + k - 1) pixel columns of k rows each, so that the column sorts are shared by the k
+windows that contain them.  The network is built as a hash-consed DAG:
+
+  1. sort every column (optimal small sorting networks, verified below);
+  2. per output: merge tree over its k sorted columns (Batcher odd-even merges; pairs of
+     columns at even positions are merged once and shared by up to four outputs), reduced to
+     the rank that matters with the two-list selection identity
+        kth(A u B) = min_{i+j=k} max(a_i, b_j);
+  3. dead-code elimination from the M median outputs.
+
+Every generated network is verified before it is written: exhaustively with the 0-1
+principle for k <= 5 (2^25 inputs per output, bit-parallel) and with random vectors for all k.
+
+Writes road-vision-system_b200/csrc/rv_median_net.h.
+"""
+import itertools
+import os
+import sys
+
+import numpy as np
+
+SORTERS = {
+    2: [(0, 1)],
+    3: [(0, 2), (0, 1), (1, 2)],
+    4: [(0, 2), (1, 3), (0, 1), (2, 3), (1, 2)],
+    5: [(0, 3), (1, 4), (0, 2), (1, 3), (0, 1), (2, 4), (1, 2), (3, 4), (2, 3)],
+    7: [(0, 6), (2, 3), (4, 5), (0, 2), (1, 4), (3, 6), (0, 1), (2, 5), (3, 4), (1, 2), (4, 6),
+        (2, 3), (4, 5), (1, 2), (3, 4), (5, 6)],
+    9: [(0, 3), (1, 7), (2, 5), (4, 8), (0, 7), (2, 4), (3, 8), (5, 6), (0, 2), (1, 3), (4, 5), (7, 8),
+        (1, 4), (3, 6), (5, 7), (0, 1), (2, 4), (3, 5), (6, 8), (2, 3), (4, 5), (6, 7), (1, 2), (3, 4), (5, 6)],
+}
+
+
+def check_sorter(n, net):
+    for bits in itertools.product((0, 1), repeat=n):
+        v = list(bits)
+        for a, b in net:
+            if v[a] > v[b]:
+                v[a], v[b] = v[b], v[a]
+        if v != sorted(v):
+            return False
+    return True
+
+
+class Dag:
+    """Hash-consed min/max expression DAG. Node ids are ints; inputs first."""
+
+    def __init__(self):
+        self.nodes = []      # (op, a, b) ; op in {"in","min","max"}
+        self.memo = {}
+
+    def inp(self, name):
+        self.nodes.append(("in", name, None))
+        return len(self.nodes) - 1
+
+    def _op(self, op, a, b):
+        if a == b:
+            return a
+        if a > b:
+            a, b = b, a
+        key = (op, a, b)
+        if key not in self.memo:
+            self.nodes.append(key)
+            self.memo[key] = len(self.nodes) - 1
+        return self.memo[key]
+
+    def mn(self, a, b): return self._op("min", a, b)
+    def mx(self, a, b): return self._op("max", a, b)
+
+    def sort(self, xs):
+        xs = list(xs)
+        for a, b in SORTERS[len(xs)]:
+            lo, hi = self.mn(xs[a], xs[b]), self.mx(xs[a], xs[b])
+            xs[a], xs[b] = lo, hi
+        return xs
+
+    def merge(self, A, B):
+        """Batcher odd-even merge of two ascending lists of arbitrary lengths (Knuth 5.3.4)."""
+        m, n = len(A), len(B)
+        if m == 0:
+            return list(B)
+        if n == 0:
+            return list(A)
+        if m == 1 and n == 1:
+            return [self.mn(A[0], B[0]), self.mx(A[0], B[0])]
+        V = self.merge(A[0::2], B[0::2])     # 1-based odd-indexed elements
+        Wl = self.merge(A[1::2], B[1::2])    # 1-based even-indexed elements
+        out = [V[0]]
+        i = 0
+        while i < len(Wl) and i + 1 < len(V):
+            out.append(self.mn(Wl[i], V[i + 1]))
+            out.append(self.mx(Wl[i], V[i + 1]))
+            i += 1
+        out.extend(Wl[i:])
+        out.extend(V[i + 1:])
+        return out
+
+    def kth2(self, A, B, k):
+        """k-th smallest (1-based) of the union of two ascending lists: min_{i+j=k} max(a_i,b_j)."""
+        terms = []
+        for i in range(0, k + 1):
+            j = k - i
+            if i > len(A) or j > len(B):
+                continue
+            if i == 0:
+                terms.append(B[j - 1])
+            elif j == 0:
+                terms.append(A[i - 1])
+            else:
+                terms.append(self.mx(A[i - 1], B[j - 1]))
+        r = terms[0]
+        for t in terms[1:]:
+            r = self.mn(r, t)
+        return r
+
+    def select_window(self, lists, lo, hi):
+        """Ascending elements of ranks lo..hi (0-based, inclusive) of a merged pair, via full merge
+        (dead code is eliminated later)."""
+        return self.merge(lists[0], lists[1])[lo:hi + 1]
+
+    def live(self, outs):
+        seen = set()
+        stack = list(outs)
+        while stack:
+            n = stack.pop()
+            if n in seen:
+                continue
+            seen.add(n)
+            op, a, b = self.nodes[n]
+            if op != "in":
+                stack.extend((a, b))
+        return seen
+
+
+def _reduce(d, groups, half, order):
+    """Merge `groups` (ascending lists) following `order` (list of index pairs into the shrinking
+    group list); returns the node holding the element of 0-based rank `half` of the union."""
+    groups = [list(g) for g in groups]
+    below = 0
+    for (i, j) in order:
+        a, b = groups[i], groups[j]
+        others = [g for t, g in enumerate(groups) if t not in (i, j)]
+        rest = sum(len(g) for g in others)
+        t = half - below
+        if not others:
+            return d.kth2(a, b, t + 1)
+        merged = d.merge(a, b)
+        lo = max(0, t - rest)                 # rank r of merged ends at final rank in [r, r + rest]
+        hi = min(len(merged) - 1, t)
+        below += lo
+        groups = [merged[lo:hi + 1]] + others
+    return groups[0][half - below]
+
+
+def _orders(n):
+    if n == 1:
+        yield []
+        return
+    for i in range(n):
+        for j in range(i + 1, n):
+            for rest in _orders(n - 1):
+                yield [(i, j)] + rest
+
+
+def reduce_best(d, groups, half):
+    """Try every merge order; keep the one that adds the fewest new nodes to the shared DAG."""
+    if len(groups) > 4:            # the order space explodes; merge the two shortest lists each time
+        order, sizes = [], [len(g) for g in groups]
+        while len(sizes) > 1:
+            idx = sorted(range(len(sizes)), key=lambda t: sizes[t])[:2]
+            i, j = min(idx), max(idx)
+            order.append((i, j))
+            rest = sum(sizes) - sizes[i] - sizes[j]
+            sizes = [min(sizes[i] + sizes[j], rest + 1)] + [s for t, s in enumerate(sizes) if t not in (i, j)]
+        return _reduce(d, groups, half, order)
+    best = None
+    for order in _orders(len(groups)):
+        n0, keys0 = len(d.nodes), set(d.memo.keys())
+        _reduce(d, groups, half, order)
+        added = len(d.nodes) - n0
+        # roll back
+        for key in set(d.memo.keys()) - keys0:
+            del d.memo[key]
+        del d.nodes[n0:]
+        if best is None or added < best[0]:
+            best = (added, order)
+    return _reduce(d, groups, half, best[1])
+
+
+def build(k, M, strategy="pairs"):
+    """Return (dag, inputs[col][row], outs[M])."""
+    d = Dag()
+    ncol = M + k - 1
+    inputs = [[d.inp((c, r)) for r in range(k)] for c in range(ncol)]
+    cols = [d.sort(col) for col in inputs]
+    half = (k * k) // 2          # 0-based rank of the median
+    pair_cache = {}
+
+    def pair(c):                 # merged columns (c, c+1); shared when c is even
+        if c not in pair_cache:
+            pair_cache[c] = d.merge(cols[c], cols[c + 1])
+        return pair_cache[c]
+
+    outs = []
+    for o in range(M):
+        cs = list(range(o, o + k))          # columns of this window
+        if strategy == "pairs":
+            # greedy pairing on even column indices so neighbouring outputs reuse the pair merges
+            groups, i = [], 0
+            while i < len(cs):
+                if cs[i] % 2 == 0 and i + 1 < len(cs):
+                    groups.append(pair(cs[i])); i += 2
+                else:
+                    groups.append(cols[cs[i]]); i += 1
+        else:
+            groups = [cols[c] for c in cs]
+        outs.append(reduce_best(d, [list(g) for g in groups], half))
+    return d, inputs, outs
+
+
+def evaluate(d, inputs, outs, values):
+    """values: dict input-node -> numpy array (any dtype supporting minimum/maximum or bit ops)."""
+    live = d.live(outs)
+    val = {}
+    for n in sorted(live):
+        op, a, b = d.nodes[n]
+        if op == "in":
+            val[n] = values[n]
+        elif op == "min":
+            val[n] = np.minimum(val[a], val[b])
+        else:
+            val[n] = np.maximum(val[a], val[b])
+    return [val[o] for o in outs]
+
+
+def verify_random(d, inputs, outs, k, M, trials=20000, seed=0):
+    rng = np.random.RandomState(seed)
+    ncol = M + k - 1
+    # mix of wide-range and few-distinct-values (ties) data
+    data = rng.randint(0, 256, (ncol, k, trials)).astype(np.int32)
+    data[:, :, : trials // 2] //= 64
+    vals = {inputs[c][r]: data[c, r] for c in range(ncol) for r in range(k)}
+    got = evaluate(d, inputs, outs, vals)
+    for o in range(M):
+        win = data[o:o + k].reshape(k * k, trials)
+        want = np.sort(win, axis=0)[(k * k) // 2]
+        if not np.array_equal(got[o], want):
+            return False
+    return True
+
+
+def verify_zero_one(d, inputs, outs, k, M):
+    """0-1 principle, exhaustive over the k*k inputs of each output (bit-parallel on uint64 words)."""
+    n = k * k
+    if n > 25:
+        return None
+    nbits = 1 << n
+    words = nbits // 64
+    # input i takes bit i of the case index
+    idx = np.arange(words, dtype=np.uint64)
+    pats = []
+    for i in range(n):
+        if i < 6:
+            base = np.uint64(sum(((j >> i) & 1) << j for j in range(64)))
+            pats.append(np.full(words, base, np.uint64))
+        else:
+            pats.append(np.where((idx >> np.uint64(i - 6)) & np.uint64(1), np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64(0)))
+    # popcount of case index >= half+1  <=> median is 1
+    pc = np.zeros(nbits, np.uint8)
+    ar = np.arange(nbits, dtype=np.uint32)
+    for i in range(n):
+        pc += ((ar >> i) & 1).astype(np.uint8)
+    want_bits = (pc >= (n // 2 + 1))
+    want = np.packbits(want_bits, bitorder="little").view(np.uint64)
+    for o in range(M):
+        live = d.live([outs[o]])
+        val = {}
+        vi = 0
+        mapping = {}
+        for c in range(o, o + k):
+            for r in range(k):
+                mapping[inputs[c][r]] = pats[vi]; vi += 1
+        for nid in sorted(live):
+            op, a, b = d.nodes[nid]
+            if op == "in":
+                val[nid] = mapping[nid]
+            elif op == "min":
+                val[nid] = val[a] & val[b]
+            else:
+                val[nid] = val[a] | val[b]
+        if not np.array_equal(val[outs[o]], want):
+            return False
+    return True
+
+
+def emit(d, inputs, outs, k, M, fh):
+    live = d.live(outs)
+    order = [n for n in sorted(live)]
+    nops = sum(1 for n in order if d.nodes[n][0] != "in")
+    ncol = M + k - 1
+    fh.write(f"/* k={k}: {M} outputs from {ncol} columns; {nops} packed min/max ops "
+             f"({nops / M:.1f} per output pair-lane) */\n")
+    fh.write(f"#define RV_MEDIAN{k}_M {M}\n#define RV_MEDIAN{k}_OPS {nops}\n")
+    fh.write(f"__device__ __forceinline__ void rv_median{k}_net(const uint32_t (&v)[{ncol}][{k}], uint32_t (&out)[{M}])\n{{\n")
+    name = {}
+    for n in order:
+        op, a, b = d.nodes[n]
+        if op == "in":
+            name[n] = f"v[{a[0]}][{a[1]}]"
+        else:
+            name[n] = f"t{n}"
+            fn = "RV_MN" if op == "min" else "RV_MX"
+            fh.write(f"    const uint32_t t{n} = {fn}({name[a]}, {name[b]});\n")
+    for o in range(M):
+        fh.write(f"    out[{o}] = {name[outs[o]]};\n")
+    fh.write("}\n\n")
+    return nops
+
+
+CONFIG = {3: 4, 5: 4, 7: 2, 9: 2}     # k -> outputs per call
+
+
+def main():
+    for n, net in SORTERS.items():
+        assert check_sorter(n, net), f"sorter {n} is wrong"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "road-vision-system_b200", "csrc", "rv_median_net.h")
+    quick = "--quick" in sys.argv
+    with open(path, "w") as fh:
+        fh.write("/* GENERATED by tools/gen_median_net.py -- do not edit.\n"
+                 " * Selection networks for the k x k median (cv2.medianBlur semantics) on packed u16x2 lanes.\n"
+                 " * v[c][r]: column c (pixel x0-k/2+c of one channel plane), row r of the window rows; any order per column.\n"
+                 " * out[o]: median of columns o..o+k-1.  Verified by the generator (0-1 principle for k<=5, random for all). */\n"
+                 "#ifndef RV_MEDIAN_NET_H\n#define RV_MEDIAN_NET_H\n#include <stdint.h>\n"
+                 "#ifndef RV_MN\n#define RV_MN(a, b) __vminu2((a), (b))\n#define RV_MX(a, b) __vmaxu2((a), (b))\n#endif\n\n")
+        for k, M in CONFIG.items():
+            best = None
+            for strat in ("pairs", "flat"):
+                d, inputs, outs = build(k, M, strat)
+                live = d.live(outs)
+                nops = sum(1 for n in live if d.nodes[n][0] != "in")
+                if best is None or nops < best[0]:
+                    best = (nops, strat, d, inputs, outs)
+            nops, strat, d, inputs, outs = best
+            assert verify_random(d, inputs, outs, k, M), f"k={k}: random verification failed"
+            if not quick:
+                z = verify_zero_one(d, inputs, outs, k, M)
+                assert z in (True, None), f"k={k}: 0-1 verification failed"
+            else:
+                z = "skipped"
+            emit(d, inputs, outs, k, M, fh)
+            print(f"k={k} M={M} strategy={strat}: {nops} ops ({nops / M:.1f}/output), zero-one={z}")
+        fh.write("#endif\n")
+    print("wrote", path)
+
+
+if __name__ == "__main__":
+    main()
