@@ -226,7 +226,10 @@ def run_gpu(args, rank, world, local_rank):
     host = np.stack([pool[(a + i) % POOL] for i in range(BATCH)])
     d_in = torch.from_numpy(host).cuda()
     d_out = torch.empty_like(d_in)
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream()          # the stream every kernel of the step is launched on; events are recorded on it
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step():
         ctx.submit_device(d_in.data_ptr(), d_out.data_ptr(), BATCH, H, W, params, stream=stream)
@@ -253,10 +256,8 @@ def run_gpu(args, rank, world, local_rank):
         step()
     e1.record()
     torch.cuda.synchronize(); barrier()
-    t1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - l0
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
     ms_max = max_over_ranks(ms)
     frames_total = sum_over_ranks(BATCH * args.steps)
     value = frames_total / (ms_max * 1e-3)
@@ -269,6 +270,14 @@ def run_gpu(args, rank, world, local_rank):
     torch.cuda.synchronize()
     kt = ctx.kernel_times(reset=True)
     ctx.set_option("kernel_timing", 0)
+    # keep the same load running until nvidia-smi (100 ms period) has seen it for >= 1.5 s, then read the clocks
+    while time.time() - t0 < 1.5:
+        step()
+        torch.cuda.synchronize()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "timed steps + per-kernel pass + same-load soak, %.2f s" % (t1 - t0)
 
     # end to end through the plugin API from pinned host memory
     pin_in, pin_out = ctx.pinned_empty(host.shape), ctx.pinned_empty(host.shape)
@@ -277,7 +286,9 @@ def run_gpu(args, rank, world, local_rank):
         {"name": "CLAHEDehaze", "params": {"space": SPACE, "clip_limit": CLIP, "tile_grid": GRID}},
         {"name": "MedianDerain", "params": {"ksize": KSIZE}}]})
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
+    if args.no_e2e:
+        e2e_steps = 0
+    for _ in range(2 if e2e_steps else 0):
         pl.process_batch(pin_in, out=pin_out)
     barrier()
     w0 = time.perf_counter()
@@ -285,10 +296,10 @@ def run_gpu(args, rank, world, local_rank):
         pl.process_batch(pin_in, out=pin_out)
         _ = int(pin_out[-1, -1, -1, 0])                       # host read of the step's result
     w1 = time.perf_counter()
-    if not np.array_equal(pin_out[0], want):
+    if e2e_steps and not np.array_equal(pin_out[0], want):
         raise SystemExit("bench: e2e output differs from the oracle")
     e2e_s = max_over_ranks(w1 - w0)
-    e2e_value = sum_over_ranks(BATCH * e2e_steps) / e2e_s
+    e2e_value = sum_over_ranks(BATCH * e2e_steps) / e2e_s if e2e_steps else None
 
     if rank != 0:
         return
@@ -343,6 +354,7 @@ def main():
     ap.add_argument("--group", type=int, default=0, help="frames per hist->lut->chain group (0 = library default)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per host pipeline chunk (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -89,9 +89,11 @@ EXPORTS = {
 
 def load_library():
     """dlopen the in-tree library and declare every symbol of include/rv_b200.h. Raises if it is missing."""
-    global _lib
+    global _lib, _SO
     with _lib_lock:
         if _lib is None:
+            if os.environ.get("RV_B200_LIB"):        # tuning builds of the same source (tools/gpu_variants.sh)
+                _SO = os.path.join(_CSRC, os.environ["RV_B200_LIB"])
             if not os.path.exists(_SO):
                 raise RvError(f"{_SO} is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(there is no CPU fallback)")

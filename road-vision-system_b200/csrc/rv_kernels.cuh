@@ -375,8 +375,11 @@ struct ChainSmem {
 };
 
 // MODE: 0 = CLAHE in YCrCb, 1 = CLAHE in LAB, 2 = no CLAHE (median only).  K: 0 (no median), 3, 5, 7, 9.
+#ifndef RV_CHAIN_MIN_CTAS
+#define RV_CHAIN_MIN_CTAS 2
+#endif
 template <int MODE, int K>
-__global__ void __launch_bounds__(CHAIN_THREADS)
+__global__ void __launch_bounds__(CHAIN_THREADS, (K <= 5 ? RV_CHAIN_MIN_CTAS : 1))
 k_chain(const ChainArgs a)
 {
     using S = ChainSmem<MODE, K>;
@@ -398,23 +401,34 @@ k_chain(const ChainArgs a)
 
     // ---- phase 0: stage the BGR box (rows clamped = BORDER_REPLICATE of the later median), tables
     {
-        const long bx0 = 3L * (x0 - LPAD);                        // first byte of the box in the row (may be < 0)
+        const int bx0 = 3 * (x0 - LPAD);                          // first byte of the box in the row (may be < 0)
         const int rowbytes = 3 * g.W;
         const bool al4 = ((reinterpret_cast<uintptr_t>(frame) & 3) == 0) && (a.spitch % 4 == 0);
-        for (int i = tid; i < BOX_H * (A_STRIDE / 4); i += CHAIN_THREADS) {
-            const int ry = i / (A_STRIDE / 4), wx = i - ry * (A_STRIDE / 4);
+        constexpr int WPR = A_STRIDE / 4;                         // 96 words per staged row = 3 per lane
+        const bool full = al4 && bx0 >= 0 && bx0 + A_STRIDE <= rowbytes;
+        for (int ry = warp; ry < BOX_H; ry += CHAIN_WARPS) {
             const int gy = min(max(y0 - R + ry, 0), g.H - 1);
-            const long b = bx0 + 4L * wx;
-            const uint8_t *rp = frame + (size_t)gy * a.spitch;
-            uint32_t v = 0;
-            if (al4 && b >= 0 && b + 4 <= rowbytes) {
-                v = __ldg(reinterpret_cast<const uint32_t *>(rp + b));
+            const uint8_t *rp = frame + (size_t)gy * a.spitch + bx0;
+            uint32_t *ar = reinterpret_cast<uint32_t *>(A + ry * A_STRIDE);
+            if (full) {
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(rp);
+                const uint32_t v0 = __ldg(rw + lane), v1 = __ldg(rw + lane + 32), v2 = __ldg(rw + lane + 64);
+                ar[lane] = v0; ar[lane + 32] = v1; ar[lane + 64] = v2;
             } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (b + k >= 0 && b + k < rowbytes) v |= (uint32_t)rp[b + k] << (8 * k);
+                for (int t = 0; t < WPR / 32; ++t) {
+                    const int wx = lane + 32 * t, b = bx0 + 4 * wx;
+                    uint32_t v = 0;
+                    if (al4 && b >= 0 && b + 4 <= rowbytes) {
+                        v = __ldg(reinterpret_cast<const uint32_t *>(rp + 4 * wx));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (b + k >= 0 && b + k < rowbytes) v |= (uint32_t)rp[4 * wx + k] << (8 * k);
+                    }
+                    ar[wx] = v;
+                }
             }
-            reinterpret_cast<uint32_t *>(A)[i] = v;
         }
     }
     // interpolation terms of this lane's four pixels (A.3), evaluated at the clamped coordinate
@@ -608,22 +622,29 @@ k_chain(const ChainArgs a)
         __syncthreads();
     }
 
-    // ---- phase 3: coalesced store of the staging tile
+    // ---- phase 3: coalesced store of the staging tile (one warp per row, three words per lane)
     {
         uint8_t *dframe = a.dst + (size_t)f * a.dfstride;
         const int nb = min(3 * TILE_W, 3 * (g.W - x0));          // valid bytes per row
         const bool al4 = ((reinterpret_cast<uintptr_t>(dframe) & 3) == 0) && (a.dpitch % 4 == 0);
         const int rows = min(TILE_H, g.H - y0);
-        for (int i = tid; i < rows * (O_STRIDE / 4); i += CHAIN_THREADS) {
-            const int ry = i / (O_STRIDE / 4), wx = i - ry * (O_STRIDE / 4);
-            const int b = 4 * wx;
-            if (b >= nb) continue;
-            uint8_t *dp = dframe + (size_t)(y0 + ry) * a.dpitch + 3 * (size_t)x0 + b;
-            const uint32_t v = *reinterpret_cast<const uint32_t *>(O + ry * O_STRIDE + b);
-            if (al4 && b + 4 <= nb) {
-                *reinterpret_cast<uint32_t *>(dp) = v;
+        constexpr int WPR = O_STRIDE / 4;                        // 90 words per row
+        for (int ry = warp; ry < rows; ry += CHAIN_WARPS) {
+            uint8_t *dp = dframe + (size_t)(y0 + ry) * a.dpitch + 3 * (size_t)x0;
+            const uint32_t *orow = reinterpret_cast<const uint32_t *>(O + ry * O_STRIDE);
+            if (al4 && nb == 3 * TILE_W) {
+                uint32_t *dw = reinterpret_cast<uint32_t *>(dp);
+                const uint32_t v0 = orow[lane], v1 = orow[lane + 32];
+                dw[lane] = v0; dw[lane + 32] = v1;
+                if (lane + 64 < WPR) dw[lane + 64] = orow[lane + 64];
             } else {
-                for (int k = 0; k < 4 && b + k < nb; ++k) dp[k] = (uint8_t)(v >> (8 * k));
+                for (int wx = lane; wx < WPR; wx += 32) {
+                    const int b = 4 * wx;
+                    if (b >= nb) break;
+                    const uint32_t v = orow[wx];
+                    if (al4 && b + 4 <= nb) *reinterpret_cast<uint32_t *>(dp + b) = v;
+                    else for (int k = 0; k < 4 && b + k < nb; ++k) dp[b + k] = (uint8_t)(v >> (8 * k));
+                }
             }
         }
     }

@@ -9,7 +9,7 @@ windows that contain them.  The network is built as a hash-consed DAG:
 
   1. sort every column (optimal small sorting networks, verified below);
   2. per output: merge tree over its k sorted columns (Batcher odd-even merges; pairs of
-     columns at even positions are merged once and shared by up to four outputs), reduced to
+     columns at even positions are merged once and shared by up to four outputs; the pairing parity is searched), reduced to
      the rank that matters with the two-list selection identity
         kth(A u B) = min_{i+j=k} max(a_i, b_j);
   3. dead-code elimination from the M median outputs.
@@ -193,7 +193,7 @@ def reduce_best(d, groups, half):
     return _reduce(d, groups, half, best[1])
 
 
-def build(k, M, strategy="pairs"):
+def build(k, M, strategy="pairs", parity=0):
     """Return (dag, inputs[col][row], outs[M])."""
     d = Dag()
     ncol = M + k - 1
@@ -214,13 +214,44 @@ def build(k, M, strategy="pairs"):
             # greedy pairing on even column indices so neighbouring outputs reuse the pair merges
             groups, i = [], 0
             while i < len(cs):
-                if cs[i] % 2 == 0 and i + 1 < len(cs):
+                if cs[i] % 2 == parity and i + 1 < len(cs):
                     groups.append(pair(cs[i])); i += 2
                 else:
                     groups.append(cols[cs[i]]); i += 1
         else:
             groups = [cols[c] for c in cs]
         outs.append(reduce_best(d, [list(g) for g in groups], half))
+    return d, inputs, outs
+
+
+def build5_quads(M, parity):
+    """5x5: columns -> pairs P(a) = merge(col a, col a+1) for a of the given parity -> quads
+    Q(a) = ranks 7..12 of merge(P(a), P(a+2)) (the only ranks of the 20 that can still be the median of
+    25) -> median = 6th smallest of Q(a) u the fifth column.  Q(a) serves outputs a and a-1, P(a)
+    serves Q(a) and Q(a-2), a sorted column serves five outputs."""
+    k = 5
+    d = Dag()
+    ncol = M + k - 1
+    inputs = [[d.inp((c, r)) for r in range(k)] for c in range(ncol)]
+    cols = [d.sort(col) for col in inputs]
+    P, Q = {}, {}
+
+    def pair(a):
+        if a not in P:
+            P[a] = d.merge(cols[a], cols[a + 1])
+        return P[a]
+
+    def quad(a):
+        if a not in Q:
+            Q[a] = d.merge(pair(a), pair(a + 2))[7:13]
+        return Q[a]
+
+    outs = []
+    for o in range(M):
+        if o % 2 == parity:
+            outs.append(d.kth2(quad(o), cols[o + 4], 6))
+        else:
+            outs.append(d.kth2(quad(o + 1), cols[o], 6))
     return d, inputs, outs
 
 
@@ -341,12 +372,17 @@ def main():
                  "#ifndef RV_MN\n#define RV_MN(a, b) __vminu2((a), (b))\n#define RV_MX(a, b) __vmaxu2((a), (b))\n#endif\n\n")
         for k, M in CONFIG.items():
             best = None
-            for strat in ("pairs", "flat"):
-                d, inputs, outs = build(k, M, strat)
+            for strat, parity in (("pairs", 0), ("pairs", 1), ("flat", 0), ("quads", 0), ("quads", 1)):
+                if strat == "quads":
+                    if k != 5:
+                        continue
+                    d, inputs, outs = build5_quads(M, parity)
+                else:
+                    d, inputs, outs = build(k, M, strat, parity)
                 live = d.live(outs)
                 nops = sum(1 for n in live if d.nodes[n][0] != "in")
                 if best is None or nops < best[0]:
-                    best = (nops, strat, d, inputs, outs)
+                    best = (nops, f"{strat}/parity{parity}", d, inputs, outs)
             nops, strat, d, inputs, outs = best
             assert verify_random(d, inputs, outs, k, M), f"k={k}: random verification failed"
             if not quick:
