@@ -303,8 +303,10 @@ int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs
 long auto_group(const rv_ctx *ctx, int h, int w)
 {
     if (ctx->group_frames > 0) return ctx->group_frames;
+    // The chain is instruction-bound, not DRAM-bound (profiles/), so a group is as large as the
+    // workspaces comfortably allow: three launches per batch, no tail effects between small groups.
     const size_t fb = (size_t)3 * w * h;
-    return std::max<long>(1, (long)((40u << 20) / fb));     // input + output of a group stay inside the 126 MB L2
+    return std::max<long>(1, std::min<long>(256, (long)(((size_t)1 << 30) / fb)));
 }
 
 long auto_chunk(const rv_ctx *ctx, int h, int w)

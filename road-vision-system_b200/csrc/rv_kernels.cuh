@@ -17,7 +17,37 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cuda_fp16.h>
+
 #include "rv_lab_tables.h"
+
+// Median compare-exchange forms.  Plane values are kept as 0x6400|v per 16-bit lane: as unsigned
+// integers they order like v (VIMNMX.U16x2, ALU pipe) and as IEEE halves they are 1024+v, exactly
+// representable together with every difference and sum used below (HFMA2/HADD2, FMA pipe).  On sm_100a both
+// pipes issue 64 lanes/clk/SM (tools/ubench_minmax.cu), so a fraction RV_FMA_NUM/RV_FMA_DEN of the
+// compare-exchanges runs on the FMA pipe:  s = relu(b - a);  max = a + s;  min = b - s.
+#ifndef RV_FMA_NUM
+#define RV_FMA_NUM 0
+#endif
+#ifndef RV_FMA_DEN
+#define RV_FMA_DEN 1
+#endif
+#define RV_PLANE_BIAS 0x64006400u
+__device__ __forceinline__ void rv_ce_fma(uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi)
+{
+    const __half2 x = *reinterpret_cast<const __half2 *>(&a), y = *reinterpret_cast<const __half2 *>(&b);
+    const uint32_t m1bits = 0xBC00BC00u;                       // (-1, -1)
+    const __half2 m1 = *reinterpret_cast<const __half2 *>(&m1bits);
+    const __half2 s = __hfma2_relu(x, m1, y);                  // relu(y - x)
+    const __half2 h = __hadd2(x, s), l = __hsub2(y, s);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+#define RV_CEX(n, lo, hi, a, b)                                            \
+    uint32_t lo, hi;                                                       \
+    if constexpr (((n) % RV_FMA_DEN) < RV_FMA_NUM) rv_ce_fma(a, b, lo, hi); \
+    else { lo = __vminu2(a, b); hi = __vmaxu2(a, b); }
+
 #include "rv_median_net.h"
 
 namespace rv {
@@ -165,21 +195,20 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
         const int gpr = g.tw >> 2;                 // 4-pixel groups per tile row
         const int total = nrows * gpr;
         const float inv_gpr = 1.0f / (float)gpr;
-        for (int idx = tid; idx < total; idx += HIST_THREADS) {
+        auto locate = [&](int idx, int &y, int &x) {
             int r = __float2int_rz(__int2float_rn(idx) * inv_gpr);
             int gx = idx - r * gpr;
             if (gx < 0) { gx += gpr; --r; }
             if (gx >= gpr) { gx -= gpr; ++r; }
-            const int y = y0 + r, x = x0 + 4 * gx;
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(frame + (size_t)y * pitch + 3 * x);
-            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+            y = y0 + r; x = x0 + 4 * gx;
+        };
+        auto process = [&](uint32_t w0, uint32_t w1, uint32_t w2, int y, int x) {
             const int B0 = w0 & 255, G0 = (w0 >> 8) & 255, R0 = (w0 >> 16) & 255;
             const int B1 = w0 >> 24, G1 = w1 & 255, R1 = (w1 >> 8) & 255;
             const int B2 = (w1 >> 16) & 255, G2 = w1 >> 24, R2 = w2 & 255;
             const int B3 = (w2 >> 8) & 255, G3 = (w2 >> 16) & 255, R3 = w2 >> 24;
             const int v0 = one(B0, G0, R0), v1 = one(B1, G1, R1), v2 = one(B2, G2, R2), v3 = one(B3, G3, R3);
             if (luma) {
-                // x is a multiple of 4 only when tw % 4 == 0 and W*y+x aligned; write bytes to stay general
                 uint8_t *lp = luma + ((size_t)f * g.H + y) * g.W + x;
                 lp[0] = (uint8_t)v0; lp[1] = (uint8_t)v1; lp[2] = (uint8_t)v2; lp[3] = (uint8_t)v3;
             }
@@ -188,6 +217,28 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
                 gmin = min(gmin, min(min(a0, a1), min(a2, a3)));
                 gmax = max(gmax, max(max(a0, a1), max(a2, a3)));
             }
+        };
+        // four 12-byte groups (48 bytes) in flight per thread: the pass is DRAM-latency bound otherwise
+        constexpr int UNR = 4;
+        int idx = tid;
+        for (; idx + (UNR - 1) * HIST_THREADS < total; idx += UNR * HIST_THREADS) {
+            uint32_t w[UNR][3];
+            int yy[UNR], xx[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                locate(idx + u * HIST_THREADS, yy[u], xx[u]);
+                const uint32_t *p = reinterpret_cast<const uint32_t *>(frame + (size_t)yy[u] * pitch + 3 * xx[u]);
+                w[u][0] = __ldg(p); w[u][1] = __ldg(p + 1); w[u][2] = __ldg(p + 2);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) process(w[u][0], w[u][1], w[u][2], yy[u], xx[u]);
+        }
+        for (; idx < total; idx += HIST_THREADS) {
+            int y, x;
+            locate(idx, y, x);
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(frame + (size_t)y * pitch + 3 * x);
+            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+            process(w0, w1, w2, y, x);
         }
     } else if (nrows > 0) {
         // generic path: ragged tiles (REFLECT_101 padding), odd tile widths, unaligned buffers
@@ -433,7 +484,7 @@ k_chain(const ChainArgs a)
     }
     // interpolation terms of this lane's four pixels (A.3), evaluated at the clamped coordinate
     float xa[4], xa1[4], cxa[4], cxa1[4];
-    int qxl[4];
+    int qxl[4], qcol[4];
     int qx_lo = 0, nqx = 1, qy_lo = 0;
     bool q_smem = true;
     const bool lane_inside = (x0 - LPAD + 4 * lane >= 0) && (x0 - LPAD + 4 * lane + 3 < g.W);
@@ -465,6 +516,7 @@ k_chain(const ChainArgs a)
             cxa[j] = -8388608.0f * xa[j];        // exact (power-of-two scale)
             cxa1[j] = -8388608.0f * xa1[j];
             qxl[j] = (int)fl + 1 - qx_lo;
+            qcol[j] = qxl[j] << 8;
         }
         for (int ry = tid; ry < BOX_H; ry += CHAIN_THREADS) {
             const int gy = min(max(y0 - R + ry, 0), g.H - 1);
@@ -472,7 +524,7 @@ k_chain(const ChainArgs a)
             const float fl = floorf(tyf);
             const float ya = __fsub_rn(tyf, fl);
             const int qy = (int)fl + 1;
-            rowp[ry] = make_float4(ya, __fsub_rn(1.0f, ya), __int_as_float(q_smem ? (qy - qy_lo) : qy), 0.f);
+            rowp[ry] = make_float4(ya, __fsub_rn(1.0f, ya), __int_as_float(q_smem ? (((qy - qy_lo) * nqx) << 8) : qy), 0.f);
         }
         if (MODE == 1) copy_lab_tabs(const_cast<LabTabs *>(tabs));
     }
@@ -480,6 +532,10 @@ k_chain(const ChainArgs a)
 
     // ---- phase 1: CLAHE on the luminance of every staged pixel (or plain unpack when MODE == 2)
     const uint32_t *qglob = (MODE != 2) ? a.quads + (size_t)f * (g.grid + 1) * (g.grid + 1) * 256 : nullptr;
+    // YCrCb results are produced UNCLAMPED with RV_BIAS16 added (K > 0): the saturation to [0,255] happens on the
+    // packed u16x2 plane words (two values per VIMNMX.S16x2) instead of per value; LAB / passthrough values are exact.
+    constexpr bool RAW = (MODE == 0) && (K > 0);
+    constexpr int OB = RAW ? 0x6400 : 0;
     auto compute_row = [&](int ry, int (&o)[12]) {
         int Bv[4], Gv[4], Rv[4];
         const uint8_t *ar = A + ry * A_STRIDE;
@@ -505,15 +561,22 @@ k_chain(const ChainArgs a)
         }
         const float4 rp = rowp[ry];
         const float ya = rp.x, ya1 = rp.y;
-        const int qyl = __float_as_int(rp.z);
+        const int qrow = __float_as_int(rp.z);                    // (local quad row * quads per row) << 8, or the global row
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int L, c1, c2;
-            if (MODE == 1) lab_fwd(tabs, Bv[j], Gv[j], Rv[j], L, c1, c2);
-            else ycrcb_fwd(Bv[j], Gv[j], Rv[j], L, c1, c2);
+            if (MODE == 1) {
+                lab_fwd(tabs, Bv[j], Gv[j], Rv[j], L, c1, c2);
+            } else {
+                // A.1 forward.  Over all 2^24 colours Cb never leaves [1,255] and Cr never goes below 0
+                // (tests/test_oracle.py::test_ycrcb_forward_ranges), so only Cr's upper bound needs a clamp.
+                L = (4899 * Rv[j] + 9617 * Gv[j] + 1868 * Bv[j] + 8192) >> 14;
+                c1 = min(((Rv[j] - L) * 11682 + ((128 << 14) + 8192)) >> 14, 255);
+                c2 = ((Bv[j] - L) * 9241 + ((128 << 14) + 8192)) >> 14;
+            }
             uint32_t q;
-            if (q_smem) q = Qs[((qyl * nqx + qxl[j]) << 8) + L];
-            else q = __ldg(qglob + (((size_t)qyl * (g.grid + 1) + (qxl[j] + qx_lo)) << 8) + L);
+            if (q_smem) q = Qs[qrow + qcol[j] + L];
+            else q = __ldg(qglob + (((size_t)qrow * (g.grid + 1) + (qxl[j] + qx_lo)) << 8) + L);
             // 0x4B0000vv = 2^23 + vv ; fma(2^23 + v, w, -2^23 * w) == v * w rounded once (A.3: no FMA contraction
             // between the products and the sums -- each step below is individually rounded)
             const float m00 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7440));
@@ -527,10 +590,25 @@ k_chain(const ChainArgs a)
             const float top = __fmul_rn(__fadd_rn(p00, p01), ya1);
             const float bot = __fmul_rn(__fadd_rn(p10, p11), ya);
             const float res = __fadd_rn(top, bot);
-            const int L2 = min(__float_as_int(__fadd_rn(res, 12582912.0f)) & 0x3FF, 255);   // round-half-even, saturate
-            if (MODE == 1) lab_inv(tabs, L2, c1, c2, o[j], o[4 + j], o[8 + j]);
-            else ycrcb_inv(L2, c1, c2, o[j], o[4 + j], o[8 + j]);
+            // round-half-even via the 1.5*2^23 trick; res <= 255*(1 + 1e-6), so the result is already in [0,255]
+            const int L2 = __float_as_int(__fadd_rn(res, 12582912.0f)) & 0x1FF;
+            if (MODE == 1) {
+                lab_inv(tabs, L2, c1, c2, o[j], o[4 + j], o[8 + j]);
+            } else {
+                // A.1 inverse with the -128 offsets folded into the rounding constants
+                const int bb = L2 + OB + ((c2 * 29049 + (8192 - 128 * 29049)) >> 14);
+                const int gg = L2 + OB + ((c2 * -5636 + c1 * -11698 + (8192 + 128 * (5636 + 11698))) >> 14);
+                const int rr = L2 + OB + ((c1 * 22987 + (8192 - 128 * 22987)) >> 14);
+                if (RAW) { o[j] = bb; o[4 + j] = gg; o[8 + j] = rr; }
+                else { o[j] = sat8(bb); o[4 + j] = sat8(gg); o[8 + j] = sat8(rr); }
+            }
         }
+    };
+    // two rows' values of one pixel/channel -> one plane word (low half = first row), saturated and biased
+    auto pack2 = [&](int lo, int hi) -> uint32_t {
+        const uint32_t w = __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
+        if (RAW) return __vmins2(__vmaxs2(w, RV_PLANE_BIAS), RV_PLANE_BIAS | 0x00FF00FFu);
+        return w | RV_PLANE_BIAS;
     };
 
     if constexpr (K == 0) {
@@ -556,10 +634,10 @@ k_chain(const ChainArgs a)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 uint4 w;
-                w.x = (uint32_t)o0[4 * c + 0] | ((uint32_t)o1[4 * c + 0] << 16);
-                w.y = (uint32_t)o0[4 * c + 1] | ((uint32_t)o1[4 * c + 1] << 16);
-                w.z = (uint32_t)o0[4 * c + 2] | ((uint32_t)o1[4 * c + 2] << 16);
-                w.w = (uint32_t)o0[4 * c + 3] | ((uint32_t)o1[4 * c + 3] << 16);
+                w.x = pack2(o0[4 * c + 0], o1[4 * c + 0]);
+                w.y = pack2(o0[4 * c + 1], o1[4 * c + 1]);
+                w.z = pack2(o0[4 * c + 2], o1[4 * c + 2]);
+                w.w = pack2(o0[4 * c + 3], o1[4 * c + 3]);
                 *reinterpret_cast<uint4 *>(P + ((size_t)c * NSLOT + s) * P_STRIDE + 4 * lane) = w;
             }
             if (s < 2 * R) {       // rows [HALF, HALF+2R) are also the low half of slots [HALF, HALF+2R)
@@ -567,10 +645,10 @@ k_chain(const ChainArgs a)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     uint4 w;
-                    w.x = (uint32_t)o1[4 * c + 0] | ((uint32_t)o0[4 * c + 0] << 16);
-                    w.y = (uint32_t)o1[4 * c + 1] | ((uint32_t)o0[4 * c + 1] << 16);
-                    w.z = (uint32_t)o1[4 * c + 2] | ((uint32_t)o0[4 * c + 2] << 16);
-                    w.w = (uint32_t)o1[4 * c + 3] | ((uint32_t)o0[4 * c + 3] << 16);
+                    w.x = pack2(o1[4 * c + 0], o0[4 * c + 0]);
+                    w.y = pack2(o1[4 * c + 1], o0[4 * c + 1]);
+                    w.z = pack2(o1[4 * c + 2], o0[4 * c + 2]);
+                    w.w = pack2(o1[4 * c + 3], o0[4 * c + 3]);
                     *reinterpret_cast<uint4 *>(P + ((size_t)c * NSLOT + s + HALF) * P_STRIDE + 4 * lane) = w;
                 }
             }
@@ -614,7 +692,7 @@ k_chain(const ChainArgs a)
 #pragma unroll
             for (int j = 0; j < M; ++j) {
                 o0[3 * j] = (uint8_t)(out[j] & 255);
-                o1[3 * j] = (uint8_t)(out[j] >> 16);
+                o1[3 * j] = (uint8_t)((out[j] >> 16) & 255);
             }
         }
         __syncthreads();

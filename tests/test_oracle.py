@@ -127,3 +127,16 @@ def test_sha_pins_full_size():
         img = np.random.RandomState(p["seed"]).randint(0, 256, (p["h"], p["w"], 3)).astype(np.uint8)
         got = O.chain(img, O.SPACE_LAB if p["space"] == "LAB" else O.SPACE_YCRCB, 2.0, p["grid"], p["k"])
         assert hashlib.sha1(got.tobytes()).hexdigest() == p["sha"], p
+
+
+def test_ycrcb_forward_ranges():
+    """The CUDA kernel drops two saturations the data can never trigger: over all 2^24 colours the un-saturated
+    forward Cb stays inside [0,255] and the un-saturated Cr never goes negative (it does exceed 255)."""
+    img = all_colours().reshape(-1, 3).astype(np.int64)
+    B, G, R = img[:, 0], img[:, 1], img[:, 2]
+    Y = (4899 * R + 9617 * G + 1868 * B + 8192) >> 14
+    cr = ((R - Y) * 11682 + (128 << 14) + 8192) >> 14
+    cb = ((B - Y) * 9241 + (128 << 14) + 8192) >> 14
+    assert Y.min() >= 0 and Y.max() <= 255
+    assert cb.min() >= 0 and cb.max() <= 255
+    assert cr.min() >= 0 and cr.max() > 255

@@ -331,19 +331,39 @@ def verify_zero_one(d, inputs, outs, k, M):
 
 
 def emit(d, inputs, outs, k, M, fh):
+    """Straight-line code. A min and a max of the same operand pair that are both live form a
+    compare-exchange and are emitted through RV_CEX(n, lo, hi, a, b) so the kernel can choose, per
+    compile-time index n, between the ALU form (2 x VIMNMX.U16x2) and the FMA-pipe form
+    (HFMA2.RELU + 2 x HADD2 on 0x6400|v half-floats); lone mins / maxes stay on the ALU pipe."""
     live = d.live(outs)
     order = [n for n in sorted(live)]
     nops = sum(1 for n in order if d.nodes[n][0] != "in")
     ncol = M + k - 1
+    partner = {}
+    for n in order:
+        op, a, b = d.nodes[n]
+        if op == "min" and ("max", a, b) in d.memo and d.memo[("max", a, b)] in live:
+            partner[n] = d.memo[("max", a, b)]
+            partner[d.memo[("max", a, b)]] = n
+    nce = len(partner) // 2
     fh.write(f"/* k={k}: {M} outputs from {ncol} columns; {nops} packed min/max ops "
-             f"({nops / M:.1f} per output pair-lane) */\n")
-    fh.write(f"#define RV_MEDIAN{k}_M {M}\n#define RV_MEDIAN{k}_OPS {nops}\n")
+             f"({nops / M:.1f} per output pair-lane), of which {nce} full compare-exchanges */\n")
+    fh.write(f"#define RV_MEDIAN{k}_M {M}\n#define RV_MEDIAN{k}_OPS {nops}\n#define RV_MEDIAN{k}_CES {nce}\n")
     fh.write(f"__device__ __forceinline__ void rv_median{k}_net(const uint32_t (&v)[{ncol}][{k}], uint32_t (&out)[{M}])\n{{\n")
-    name = {}
+    name, done, ce = {}, set(), 0
     for n in order:
         op, a, b = d.nodes[n]
         if op == "in":
             name[n] = f"v[{a[0]}][{a[1]}]"
+            continue
+        if n in done:
+            continue
+        if n in partner:
+            lo, hi = (n, partner[n]) if op == "min" else (partner[n], n)
+            name[lo], name[hi] = f"t{lo}", f"t{hi}"
+            fh.write(f"    RV_CEX({ce}, t{lo}, t{hi}, {name[a]}, {name[b]});\n")
+            done.update((lo, hi))
+            ce += 1
         else:
             name[n] = f"t{n}"
             fn = "RV_MN" if op == "min" else "RV_MX"
@@ -369,7 +389,8 @@ def main():
                  " * v[c][r]: column c (pixel x0-k/2+c of one channel plane), row r of the window rows; any order per column.\n"
                  " * out[o]: median of columns o..o+k-1.  Verified by the generator (0-1 principle for k<=5, random for all). */\n"
                  "#ifndef RV_MEDIAN_NET_H\n#define RV_MEDIAN_NET_H\n#include <stdint.h>\n"
-                 "#ifndef RV_MN\n#define RV_MN(a, b) __vminu2((a), (b))\n#define RV_MX(a, b) __vmaxu2((a), (b))\n#endif\n\n")
+                 "#ifndef RV_MN\n#define RV_MN(a, b) __vminu2((a), (b))\n#define RV_MX(a, b) __vmaxu2((a), (b))\n#endif\n"
+                 "#ifndef RV_CEX\n#define RV_CEX(n, lo, hi, a, b) const uint32_t lo = RV_MN(a, b), hi = RV_MX(a, b)\n#endif\n\n")
         for k, M in CONFIG.items():
             best = None
             for strat, parity in (("pairs", 0), ("pairs", 1), ("flat", 0), ("quads", 0), ("quads", 1)):
