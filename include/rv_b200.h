@@ -74,7 +74,7 @@ const char *rv_last_error(const rv_ctx *ctx);
 
 /* tuning knobs: "group_frames" (frames per hist->lut->apply pass, sized for L2 residency),
  * "chunk_frames" (frames per H2D/compute/D2H pipeline stage for host memory), 0 = automatic;
- * "kernel_timing" (0/1, see rv_kernel_time). */
+ * "kernel_timing" (0/1, see rv_kernel_time); "use_tma" (default 1; 0 forces the plain-load staging path). */
 int rv_set_option(rv_ctx *ctx, const char *name, long value);
 /* kernels launched by this context since creation (for bench accounting) */
 long rv_launch_count(const rv_ctx *ctx);

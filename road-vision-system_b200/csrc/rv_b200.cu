@@ -47,6 +47,7 @@ struct rv_ctx {
     Buf scratch;                            // stage-level calls
     long launches = 0;
     long group_frames = 0, chunk_frames = 0;
+    long use_tma = 1;                       // stage k_chain's box with TMA when the source buffer is 16-byte aligned
     long kernel_timing = 0;                 // bracket hist / lut / chain launches with events
     std::vector<TimedLaunch> timed;         // pending (not yet read) event pairs
     std::vector<cudaEvent_t> ev_pool;
@@ -162,10 +163,51 @@ int check_params(rv_ctx *ctx, const rv_params *p)
     return RV_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// Tensor map over the source frames as u32 words: dims (3W/4, H, n), box (A_STRIDE/4 = 100, box_h, 1).  Returns false when the
+// buffer does not meet TMA's alignment rules (the kernel then stages with ordinary loads).
+bool make_src_map(const ChainArgs &a, int n, int box_h, CUtensorMap *map)
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const uintptr_t base = reinterpret_cast<uintptr_t>(a.src);
+    if ((base & 15) || (a.spitch & 15) || (a.sfstride & 15) || (3 * a.g.W) % 4) return false;
+    if (3 * a.g.W / 4 < A_STRIDE / 4 || a.g.H < box_h) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)(3 * a.g.W / 4), (cuuint64_t)a.g.H, (cuuint64_t)n};
+    cuuint64_t strides[2] = {(cuuint64_t)a.spitch, (cuuint64_t)(n > 1 ? a.sfstride : a.spitch * a.g.H)};
+    cuuint32_t box[3] = {(cuuint32_t)(A_STRIDE / 4), (cuuint32_t)box_h, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t *>(a.src), dims, strides, box, es,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int MODE, int K>
-int launch_chain_t(rv_ctx *ctx, const ChainArgs &a, int n, cudaStream_t st)
+int launch_chain_t(rv_ctx *ctx, const ChainArgs &a0, int n, cudaStream_t st)
 {
     using S = ChainSmem<MODE, K>;
+    ChainArgs a = a0;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    a.use_tma = (ctx->use_tma && make_src_map(a, n, S::BOX_H, &tmap)) ? 1 : 0;
     static bool configured[64] = {};
     if (!configured[ctx->device & 63]) {
         CK(cudaFuncSetAttribute(k_chain<MODE, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
@@ -174,7 +216,7 @@ int launch_chain_t(rv_ctx *ctx, const ChainArgs &a, int n, cudaStream_t st)
     dim3 grid((a.g.W + TILE_W - 1) / TILE_W, (a.g.H + TILE_H - 1) / TILE_H, n);
     {
         ScopedTiming tm(ctx, st, 2);
-        k_chain<MODE, K><<<grid, CHAIN_THREADS, S::total, st>>>(a);
+        k_chain<MODE, K><<<grid, CHAIN_THREADS, S::total, st>>>(a, tmap);
     }
     ctx->launches++;
     CK(cudaGetLastError());
@@ -252,7 +294,7 @@ int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs
     ChainArgs a;
     a.src = din; a.spitch = ipitch; a.sfstride = ifs;
     a.dst = dout; a.dpitch = opitch; a.dfstride = ofs;
-    a.quads = nullptr; a.flags = nullptr;
+    a.quads = nullptr; a.flags = nullptr; a.use_tma = 0;
     if (flags_out) *flags_out = nullptr;
     if (!p->clahe) {
         a.g = make_geo(h, w, 2);
@@ -485,6 +527,7 @@ int rv_set_option(rv_ctx *ctx, const char *name, long value)
     if (strcmp(name, "group_frames") == 0) { ctx->group_frames = value; return RV_OK; }
     if (strcmp(name, "chunk_frames") == 0) { ctx->chunk_frames = value; return RV_OK; }
     if (strcmp(name, "kernel_timing") == 0) { ctx->kernel_timing = value; return RV_OK; }
+    if (strcmp(name, "use_tma") == 0) { ctx->use_tma = value; return RV_OK; }
     return fail(ctx, RV_ERR_ARG, "unknown option '%s'", name);
 }
 

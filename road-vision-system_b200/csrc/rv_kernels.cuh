@@ -14,6 +14,7 @@
  *                 shared-memory tile (packed u16x2 selection network), coalesced store
  */
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -369,6 +370,36 @@ __global__ void k_gate_copy(const uint8_t *__restrict__ src, size_t spitch, size
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk.tensor) + mbarrier helpers for the box staging of k_chain
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (int spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (spin > (1 << 22)) __trap();          // a lost TMA must fail loudly, never hang the GPU
+    }
+}
+// 3-D tiled load: box -> dense shared memory, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3+K4: fused apply (+ inverse colour) + median.
 // ---------------------------------------------------------------------------------------------
 constexpr int TILE_W = 120;            // output pixels per tile row
@@ -378,7 +409,8 @@ constexpr int TILE_H = 32;
 constexpr int HALF = TILE_H / 2;       // u16x2 lanes of the median hold rows (s, s + HALF)
 constexpr int CHAIN_THREADS = 256;
 constexpr int CHAIN_WARPS = CHAIN_THREADS / 32;
-constexpr int A_STRIDE = BOX_W * 3;    // bytes per staged BGR row
+constexpr int A_STRIDE = BOX_W * 3 + 16; // bytes per staged BGR row: the box starts at the 16-byte boundary at or below
+                                       // pixel x0-LPAD (a TMA box must start 16-byte aligned), so up to 12 bytes of slack
 constexpr int P_STRIDE = BOX_W;        // words per plane row (one u16x2 word per pixel)
 constexpr int O_STRIDE = TILE_W * 3;   // bytes per output staging row
 constexpr int MAXQ = 6;                // quad tables kept in shared memory per CTA
@@ -389,6 +421,7 @@ struct ChainArgs {
     Geo g;
     const uint32_t *quads;             // [frames][(grid+1)^2][256]
     const int32_t *flags;              // optional per-frame gate flags (0 = skip frame)
+    int use_tma;                       // stage the box with one cp.async.bulk.tensor per CTA (aligned buffers)
 };
 
 template <int K> struct MedianCfg;
@@ -431,11 +464,12 @@ struct ChainSmem {
 #endif
 template <int MODE, int K>
 __global__ void __launch_bounds__(CHAIN_THREADS, (K <= 5 ? RV_CHAIN_MIN_CTAS : 1))
-k_chain(const ChainArgs a)
+k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
 {
     using S = ChainSmem<MODE, K>;
     constexpr int R = S::R, BOX_H = S::BOX_H;
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t tma_bar;
     uint8_t *A = smem + S::off_a;
     uint32_t *P = reinterpret_cast<uint32_t *>(smem + S::off_p);
     float4 *rowp = reinterpret_cast<float4 *>(smem + S::off_row);
@@ -450,25 +484,38 @@ k_chain(const ChainArgs a)
     const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const uint8_t *frame = a.src + (size_t)f * a.sfstride;
 
-    // ---- phase 0: stage the BGR box (rows clamped = BORDER_REPLICATE of the later median), tables
-    {
-        const int bx0 = 3 * (x0 - LPAD);                          // first byte of the box in the row (may be < 0)
+    // ---- phase 0: stage the BGR box: rows y0-R .. y0-R+BOX_H-1 (rows outside the frame are never read:
+    // compute_row clamps the row index = BORDER_REPLICATE of the later median); bytes from the 16-byte boundary
+    // at or below 3*(x0-LPAD) (`aoff` bytes of slack, 4 or 12), A_STRIDE bytes per row.
+    const int aoff = (3 * (x0 - LPAD)) & 15;
+    const int bx0 = 3 * (x0 - LPAD) - aoff;                       // first staged byte of each row (may be < 0)
+    if (a.use_tma) {
+        // one TMA box per CTA: 100 u32 x BOX_H rows of frame f; out-of-range parts are zero-filled by the hardware
+        if (tid == 0) mbar_init(&tma_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&tma_bar, (uint32_t)(BOX_H * A_STRIDE));
+            tma_load_3d(A, &tmap, &tma_bar, bx0 / 4, y0 - R, f);
+        }
+    } else {
         const int rowbytes = 3 * g.W;
         const bool al4 = ((reinterpret_cast<uintptr_t>(frame) & 3) == 0) && (a.spitch % 4 == 0);
-        constexpr int WPR = A_STRIDE / 4;                         // 96 words per staged row = 3 per lane
+        constexpr int WPR = A_STRIDE / 4;                         // 100 words per staged row
         const bool full = al4 && bx0 >= 0 && bx0 + A_STRIDE <= rowbytes;
         for (int ry = warp; ry < BOX_H; ry += CHAIN_WARPS) {
-            const int gy = min(max(y0 - R + ry, 0), g.H - 1);
+            const int gy = y0 - R + ry;
+            if (gy < 0 || gy >= g.H) continue;
             const uint8_t *rp = frame + (size_t)gy * a.spitch + bx0;
             uint32_t *ar = reinterpret_cast<uint32_t *>(A + ry * A_STRIDE);
             if (full) {
                 const uint32_t *rw = reinterpret_cast<const uint32_t *>(rp);
                 const uint32_t v0 = __ldg(rw + lane), v1 = __ldg(rw + lane + 32), v2 = __ldg(rw + lane + 64);
                 ar[lane] = v0; ar[lane + 32] = v1; ar[lane + 64] = v2;
+                if (lane + 96 < WPR) ar[lane + 96] = __ldg(rw + lane + 96);
             } else {
-#pragma unroll
-                for (int t = 0; t < WPR / 32; ++t) {
-                    const int wx = lane + 32 * t, b = bx0 + 4 * wx;
+                for (int wx = lane; wx < WPR; wx += 32) {
+                    const int b = bx0 + 4 * wx;
                     uint32_t v = 0;
                     if (al4 && b >= 0 && b + 4 <= rowbytes) {
                         v = __ldg(reinterpret_cast<const uint32_t *>(rp + 4 * wx));
@@ -524,10 +571,12 @@ k_chain(const ChainArgs a)
             const float fl = floorf(tyf);
             const float ya = __fsub_rn(tyf, fl);
             const int qy = (int)fl + 1;
-            rowp[ry] = make_float4(ya, __fsub_rn(1.0f, ya), __int_as_float(q_smem ? (((qy - qy_lo) * nqx) << 8) : qy), 0.f);
+            rowp[ry] = make_float4(ya, __fsub_rn(1.0f, ya), __int_as_float(q_smem ? (((qy - qy_lo) * nqx) << 8) : qy),
+                                   __int_as_float((gy - (y0 - R)) * A_STRIDE));
         }
         if (MODE == 1) copy_lab_tabs(const_cast<LabTabs *>(tabs));
     }
+    if (a.use_tma) mbar_wait(&tma_bar, 0);
     __syncthreads();
 
     // ---- phase 1: CLAHE on the luminance of every staged pixel (or plain unpack when MODE == 2)
@@ -538,9 +587,16 @@ k_chain(const ChainArgs a)
     constexpr int OB = RAW ? 0x6400 : 0;
     auto compute_row = [&](int ry, int (&o)[12]) {
         int Bv[4], Gv[4], Rv[4];
-        const uint8_t *ar = A + ry * A_STRIDE;
+        float4 rp;
+        const uint8_t *ar;
+        if (MODE == 2) {
+            ar = A + (min(max(y0 - R + ry, 0), g.H - 1) - (y0 - R)) * A_STRIDE;
+        } else {
+            rp = rowp[ry];
+            ar = A + __float_as_int(rp.w);                 // staged row of the clamped image row
+        }
         if (lane_inside) {
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(ar + 12 * lane);
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(ar + aoff + 12 * lane);
             const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
             Bv[0] = w0 & 255; Gv[0] = (w0 >> 8) & 255; Rv[0] = (w0 >> 16) & 255;
             Bv[1] = w0 >> 24; Gv[1] = w1 & 255; Rv[1] = (w1 >> 8) & 255;
@@ -550,7 +606,7 @@ k_chain(const ChainArgs a)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int cx = min(max(x0 - LPAD + 4 * lane + j, 0), g.W - 1);
-                const uint8_t *p = ar + 3 * (cx - (x0 - LPAD));
+                const uint8_t *p = ar + aoff + 3 * (cx - (x0 - LPAD));
                 Bv[j] = p[0]; Gv[j] = p[1]; Rv[j] = p[2];
             }
         }
@@ -559,7 +615,6 @@ k_chain(const ChainArgs a)
             for (int j = 0; j < 4; ++j) { o[j] = Bv[j]; o[4 + j] = Gv[j]; o[8 + j] = Rv[j]; }
             return;
         }
-        const float4 rp = rowp[ry];
         const float ya = rp.x, ya1 = rp.y;
         const int qrow = __float_as_int(rp.z);                    // (local quad row * quads per row) << 8, or the global row
 #pragma unroll
@@ -638,7 +693,7 @@ k_chain(const ChainArgs a)
                 w.y = pack2(o0[4 * c + 1], o1[4 * c + 1]);
                 w.z = pack2(o0[4 * c + 2], o1[4 * c + 2]);
                 w.w = pack2(o0[4 * c + 3], o1[4 * c + 3]);
-                *reinterpret_cast<uint4 *>(P + ((size_t)c * NSLOT + s) * P_STRIDE + 4 * lane) = w;
+                *reinterpret_cast<uint4 *>(P + (c * NSLOT + s) * P_STRIDE + 4 * lane) = w;
             }
             if (s < 2 * R) {       // rows [HALF, HALF+2R) are also the low half of slots [HALF, HALF+2R)
                 compute_row(s + TILE_H, o0);
@@ -649,7 +704,7 @@ k_chain(const ChainArgs a)
                     w.y = pack2(o1[4 * c + 1], o0[4 * c + 1]);
                     w.z = pack2(o1[4 * c + 2], o0[4 * c + 2]);
                     w.w = pack2(o1[4 * c + 3], o0[4 * c + 3]);
-                    *reinterpret_cast<uint4 *>(P + ((size_t)c * NSLOT + s + HALF) * P_STRIDE + 4 * lane) = w;
+                    *reinterpret_cast<uint4 *>(P + (c * NSLOT + s + HALF) * P_STRIDE + 4 * lane) = w;
                 }
             }
         }
@@ -669,7 +724,7 @@ k_chain(const ChainArgs a)
             if (x0 + M * m >= g.W) continue;
             if (y0 + s >= g.H) continue;
             uint32_t v[NC][K];
-            const uint32_t *pc = P + ((size_t)c * NSLOT + s) * P_STRIDE;
+            const uint32_t *pc = P + (c * NSLOT + s) * P_STRIDE;
             if (M == 4) {
 #pragma unroll
                 for (int d = 0; d < K; ++d) {

@@ -238,3 +238,20 @@ def test_size_independent_properties_full_batch(ctx):
     assert np.array_equal(got[0], O.chain(pool[0], O.SPACE_YCRCB, 2.0, 8, 5))
     const = np.full((1, 1080, 1920, 3), 77, np.uint8)
     assert np.array_equal(ctx.median(const, 5), const)
+
+
+def test_tma_and_plain_staging_agree(ctx):
+    """k_chain stages its box with one TMA load per CTA on aligned buffers; the plain-load path must give the same bytes."""
+    import rvb200
+    from rvb200 import synth
+    frames = synth.frame_pool(360, 640, 3, base_seed=70)
+    p = rvb200.Params.make("YCrCb", 2.0, 8, 5)
+    a = ctx.chain(frames, p)
+    ctx.set_option("use_tma", 0)
+    try:
+        b = ctx.chain(frames, p)
+    finally:
+        ctx.set_option("use_tma", 1)
+    assert np.array_equal(a, b)
+    for i in range(3):
+        assert np.array_equal(a[i], O.chain(frames[i], O.SPACE_YCRCB, 2.0, 8, 5))

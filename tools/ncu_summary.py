@@ -1,0 +1,70 @@
+#!/usr/bin/env python3
+"""Summarise an .ncu-rep (read here, no GPU needed): headline metrics + SASS instruction mix per phase.
+usage: tools/ncu_summary.py gpurun_out/prof_chain_TAG.ncu-rep [out.txt]"""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__registers_per_thread', 'launch__occupancy_limit_registers',
+        'launch__occupancy_limit_shared_mem', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_sector_hit_rate.pct',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'smsp__inst_executed.sum', 'smsp__thread_inst_executed.sum',
+        'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'l1tex__throughput.avg.pct_of_peak_sustained_active', 'sm__cycles_elapsed.max']
+
+
+def ncu(rep, page):
+    out = subprocess.run(['ncu', '-i', rep, '--page', page, '--csv'], capture_output=True, text=True).stdout
+    return list(csv.reader(io.StringIO(out)))
+
+
+def main():
+    rep = sys.argv[1]
+    out = open(sys.argv[2], 'w') if len(sys.argv) > 2 else sys.stdout
+    rows = ncu(rep, 'raw')
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    d = data[0]
+    print(f"# {rep}\nkernel: {d[hdr.index('Kernel Name')]}", file=out)
+    for w in WANT:
+        if w in hdr:
+            i = hdr.index(w)
+            print(f"{w:72s} {d[i]:>16s} {units[i]}", file=out)
+    stalls = [(hdr[i], float(d[i])) for i in range(len(hdr)) if hdr[i].startswith('smsp__average_warps_issue_stalled') and hdr[i].endswith('_per_issue_active.ratio') and d[i]]
+    if not stalls:
+        stalls = [(hdr[i], float(d[i])) for i in range(len(hdr)) if 'issue_stalled' in hdr[i] and hdr[i].endswith('.pct') and d[i]]
+    print("\nwarp stall reasons (top):", file=out)
+    for k, v in sorted(stalls, key=lambda kv: -kv[1])[:8]:
+        print(f"  {k:90s} {v:10.3f}", file=out)
+    rows = ncu(rep, 'source')
+    hidx = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
+    if not hidx:
+        return
+    h = rows[hidx[0]]
+    end = hidx[1] - 1 if len(hidx) > 1 else len(rows)
+    body = rows[hidx[0] + 1:end]
+    iS, iI, iSm = h.index('Source'), h.index('Instructions Executed'), h.index('# Samples')
+    tot, byop, samp, acc, phases = 0, collections.Counter(), collections.Counter(), 0, []
+    for r in body:
+        if len(r) <= iI or not r[iI]:
+            continue
+        n = int(r[iI]); tot += n
+        toks = r[iS].split()
+        op = (toks[1] if toks[0].startswith('@') else toks[0]).split('.')[0]
+        byop[op] += n; samp[op] += int(r[iSm] or 0)
+        acc += n
+        if op == 'BAR':
+            phases.append(acc)
+    print(f"\nwarp instructions executed: {tot}", file=out)
+    print("cumulative share at each BAR.SYNC: " + ", ".join(f"{100 * x / tot:.1f}%" for x in phases), file=out)
+    for op, n in byop.most_common(22):
+        print(f"  {op:12s} {n:12d} {100 * n / tot:5.1f}%   stall samples {samp[op]}", file=out)
+
+
+if __name__ == '__main__':
+    main()
