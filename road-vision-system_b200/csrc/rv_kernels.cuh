@@ -725,20 +725,33 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             if (y0 + s >= g.H) continue;
             uint32_t v[NC][K];
             const uint32_t *pc = P + (c * NSLOT + s) * P_STRIDE;
-            if (M == 4) {
+            constexpr int C0 = LPAD - R;                 // first needed plane word, relative to the group's first output
+            if constexpr (M == 4) {
+                // 16-byte loads of words 4m .. 4m+11 (conflict-free: 8 lanes x 16 B per phase)
 #pragma unroll
                 for (int d = 0; d < K; ++d) {
                     const uint4 *p4 = reinterpret_cast<const uint4 *>(pc + d * P_STRIDE + 4 * m);
                     const uint4 q0 = p4[0], q1 = p4[1], q2 = p4[2];
                     const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
-                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[LPAD - R + cc];
+                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[C0 + cc];
+                }
+            } else if constexpr (C0 % 2 == 0 && M % 2 == 0 && NC % 2 == 0) {
+                // 8-byte loads; with M = 6 the 16 lanes of a phase hit 16 distinct even banks (6m+2 mod 32)
+#pragma unroll
+                for (int d = 0; d < K; ++d) {
+                    const uint2 *p2 = reinterpret_cast<const uint2 *>(pc + d * P_STRIDE + M * m + C0);
+#pragma unroll
+                    for (int cc = 0; cc < NC / 2; ++cc) {
+                        const uint2 q = p2[cc];
+                        v[2 * cc][d] = q.x; v[2 * cc + 1][d] = q.y;
+                    }
                 }
             } else {
 #pragma unroll
                 for (int d = 0; d < K; ++d)
 #pragma unroll
-                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = pc[d * P_STRIDE + LPAD + M * m - R + cc];
+                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = pc[d * P_STRIDE + M * m + C0 + cc];
             }
             uint32_t out[M];
             median_net<K, NC, M>(v, out);

@@ -374,7 +374,7 @@ def emit(d, inputs, outs, k, M, fh):
     return nops
 
 
-CONFIG = {3: 4, 5: 4, 7: 2, 9: 2}     # k -> outputs per call
+CONFIG = {3: 4, 5: int(os.environ.get('RV_MEDIAN5_M', '6')), 7: 2, 9: 2}     # k -> outputs per call
 
 
 def main():
