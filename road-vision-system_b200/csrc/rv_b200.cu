@@ -262,10 +262,14 @@ int launch_hist(rv_ctx *ctx, const uint8_t *src, size_t pitch, size_t fstride, c
     dim3 grid(slices, tiles, n);
     {
         ScopedTiming tm(ctx, st, 0);
-        if (space == RV_SPACE_LAB)
-            k_luma_hist<1><<<grid, HIST_THREADS, 0, st>>>(src, pitch, fstride, g, rps, hist, luma, mm);
-        else
-            k_luma_hist<0><<<grid, HIST_THREADS, 0, st>>>(src, pitch, fstride, g, rps, hist, luma, mm);
+        const bool extra = luma != nullptr || mm != nullptr;
+        if (space == RV_SPACE_LAB) {
+            if (extra) k_luma_hist<1, true><<<grid, HIST_THREADS, 0, st>>>(src, pitch, fstride, g, rps, hist, luma, mm);
+            else k_luma_hist<1, false><<<grid, HIST_THREADS, 0, st>>>(src, pitch, fstride, g, rps, hist, luma, mm);
+        } else {
+            if (extra) k_luma_hist<0, true><<<grid, HIST_THREADS, 0, st>>>(src, pitch, fstride, g, rps, hist, luma, mm);
+            else k_luma_hist<0, false><<<grid, HIST_THREADS, 0, st>>>(src, pitch, fstride, g, rps, hist, luma, mm);
+        }
     }
     ctx->launches++;
     CK(cudaGetLastError());

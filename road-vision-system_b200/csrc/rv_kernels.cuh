@@ -34,6 +34,9 @@
 #define RV_FMA_DEN 1
 #endif
 #define RV_PLANE_BIAS 0x64006400u
+#ifndef RV_HIST_DP4A
+#define RV_HIST_DP4A 1
+#endif
 __device__ __forceinline__ void rv_ce_fma(uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi)
 {
     const __half2 x = *reinterpret_cast<const __half2 *>(&a), y = *reinterpret_cast<const __half2 *>(&b);
@@ -157,11 +160,14 @@ __device__ __forceinline__ void copy_lab_tabs(LabTabs *dst)
 constexpr int HIST_THREADS = 256;
 constexpr int HIST_WARPS = HIST_THREADS / 32;
 
-template <int SPACE>
+// EXTRA = false is the production instantiation (no luma plane, no gray min/max: nothing but the histogram).
+template <int SPACE, bool EXTRA>
 __global__ void __launch_bounds__(HIST_THREADS)
 k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g, int rows_per_slice,
-            int32_t *__restrict__ hist, uint8_t *__restrict__ luma, int32_t *__restrict__ gray_minmax)
+            int32_t *__restrict__ hist, uint8_t *__restrict__ luma_arg, int32_t *__restrict__ gray_arg)
 {
+    uint8_t *const luma = EXTRA ? luma_arg : nullptr;
+    int32_t *const gray_minmax = EXTRA ? gray_arg : nullptr;
     __shared__ uint32_t wh[HIST_WARPS][256];
     __shared__ __align__(16) unsigned char tab_raw[SPACE == 1 ? sizeof(LabTabs) : 16];
     LabTabs *tabs = reinterpret_cast<LabTabs *>(tab_raw);
@@ -204,6 +210,21 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
             y = y0 + r; x = x0 + 4 * gx;
         };
         auto process = [&](uint32_t w0, uint32_t w1, uint32_t w2, int y, int x) {
+#if RV_HIST_DP4A
+            if (SPACE == 0 && !EXTRA) {
+                // Y = (4899 R + 9617 G + 1868 B + 8192) >> 14 as two byte dot products per pixel on the packed BGRx word
+                // (coefficients split into low and high bytes), no per-channel unpacking
+                const uint32_t p0 = w0, p1 = __funnelshift_r(w0, w1, 24), p2 = __funnelshift_r(w1, w2, 16), p3 = w2 >> 8;
+                constexpr uint32_t LO = 76u | (145u << 8) | (35u << 16), HI = 7u | (37u << 8) | (19u << 16);
+                const uint32_t pp[4] = {p0, p1, p2, p3};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t v = (__dp4a(pp[j], LO, 8192u) + (__dp4a(pp[j], HI, 0u) << 8)) >> 14;
+                    atomicAdd(&myh[v], 1u);
+                }
+                return;
+            }
+#endif
             const int B0 = w0 & 255, G0 = (w0 >> 8) & 255, R0 = (w0 >> 16) & 255;
             const int B1 = w0 >> 24, G1 = w1 & 255, R1 = (w1 >> 8) & 255;
             const int B2 = (w1 >> 16) & 255, G2 = w1 >> 24, R2 = w2 & 255;

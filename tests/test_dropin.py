@@ -55,17 +55,25 @@ def test_stock_yaml_builds_the_pipeline(tmp_path):
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 
-@needs_ref
 @pytest.mark.gpu
-def test_stock_yaml_runs_on_gpu(tmp_path):
-    tmp = make_tree(tmp_path)
-    r = run(tmp, """
+def test_stock_chain_runs_on_gpu_as_src_preprocess(tmp_path):
+    """GPU half (the GPU box has no /root/reference): same mount as `src/preprocess`, config = the `preprocess:` block of
+    configs/default.yaml:21-34 spelled out; the loader + YAML themselves are covered by the CPU test above."""
+    src = tmp_path / "src"
+    src.mkdir()
+    (src / "__init__.py").write_text("")
+    for name in ("preprocess", "io_video", "_native.py", "csrc", "synth.py"):
+        os.symlink(os.path.join(PKG, name), src / name)
+    r = run(tmp_path, """
         import numpy as np
-        from src.config import load_config
-        from src.preprocess import PreprocessPipeline
+        from src.preprocess import PreprocessPipeline         # main_preview.py:6
         from src import synth
         from oracle import rv_oracle as O
-        pipe = PreprocessPipeline(load_config()["preprocess"])
+        pp = {"enabled": True,
+              "chain": [{"name": "CLAHEDehaze", "params": {"space": "YCrCb", "clip_limit": 2.0, "tile_grid": 8}},
+                        {"name": "MedianDerain", "params": {"ksize": 3}}],
+              "auto_gate": {"enable_low_contrast_gate": False, "contrast_thresh": 20.0}}
+        pipe = PreprocessPipeline(pp)                         # main_preview.py:58
         raw = synth.road_frame(480, 640, 1)                   # default.yaml:3-4 camera size
         keep = raw.copy()
         proc = pipe(raw, ts=0.0)                              # main_preview.py:94
