@@ -118,6 +118,20 @@ int rv_clahe_dehaze(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, 
                     size_t in_pitch, size_t out_pitch, int space, double clip_limit, int grid, int mem_kind);
 int rv_median(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w,
               size_t in_pitch, size_t out_pitch, int ksize, int mem_kind);
+/* ---- detector-input stage (the step right after the chain: detector.infer(proc), main_preview.py:99 ->
+ * ultralytics' LetterBox + BGR->RGB + HWC->CHW + /255 + half inside model.predict, src/detect/yolo_ultralytics.py:28-35).
+ * Square letterbox to S x S: r = min(S/h, S/w), new size round(w r) x round(h r), centred (extra row/column at the
+ * bottom/right), constant padding, cv2.resize(INTER_LINEAR) 8-bit arithmetic.  out: n*3*S*S IEEE halves (RGB planes).
+ * ultralytics is not installed here and unpinned in the reference: the geometry is this documented spec ("parity
+ * unpinned" for it); the resize arithmetic is pinned bit-exactly against cv2.resize. */
+int rv_letterbox_geometry(int h, int w, int S, int32_t *new_w, int32_t *new_h, int32_t *top, int32_t *left, int32_t *fused_scale);
+int rv_letterbox_f16(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t pitch, uint16_t *out, int S, int pad_value, int mem_kind);
+/* chain + detector input in one call.  full_out (optional) also receives the full-resolution BGR result; when it is NULL
+ * and the down-scale is an exact integer (1080p -> 640: 3) the full-resolution frame is never written at all (the
+ * resize is fused into the chain kernel's store phase).  stream: as rv_submit (RV_MEM_DEVICE: asynchronous if given). */
+int rv_chain_letterbox_f16(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t in_pitch, const rv_params *p,
+                           uint16_t *out, int S, int pad_value, uint8_t *full_out, size_t full_pitch, int mem_kind, void *stream);
+
 /* span: n ints = max(gray) - min(gray) per frame */
 int rv_gray_span(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t pitch, int32_t *span, int mem_kind);
 

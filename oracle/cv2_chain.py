@@ -54,3 +54,18 @@ def low_contrast(image, thresh=20.0):
     """pipeline.py:24-30"""
     gray = cv2.cvtColor(image, cv2.COLOR_BGR2GRAY)
     return (int(gray.max()) - int(gray.min())) < float(thresh)
+
+
+def letterbox_f16(image, size=640, pad_value=114):
+    """Detector input as ultralytics prepares it inside model.predict (yolo_ultralytics.py:28-35): LetterBox (cv2.resize
+    INTER_LINEAR + cv2.copyMakeBorder 114), BGR->RGB, HWC->CHW, /255, half.  ultralytics itself is not installed; the
+    geometry follows its LetterBox with auto=False, scaleup=True, center=True."""
+    h, w = image.shape[:2]
+    r = min(size / h, size / w)
+    nw, nh = max(1, int(round(w * r))), max(1, int(round(h * r)))
+    dw, dh = (size - nw) / 2, (size - nh) / 2
+    img = cv2.resize(image, (nw, nh), interpolation=cv2.INTER_LINEAR) if (w, h) != (nw, nh) else image
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    img = cv2.copyMakeBorder(img, top, bottom, left, right, cv2.BORDER_CONSTANT, value=(pad_value,) * 3)
+    return (np.ascontiguousarray(img[:, :, ::-1].transpose(2, 0, 1)).astype(np.float32) / np.float32(255)).astype(np.float16)

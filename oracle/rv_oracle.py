@@ -151,3 +151,50 @@ def chain(img, space, clip_limit, grid, ksize):
     if lib().rvo_chain(_p(img), H, W, space, float(clip_limit), grid, ksize, _p(out)) != 0:
         raise MemoryError
     return out
+
+
+# ---------------------------------------------------------------- detector-input stage
+def letterbox_geometry(h, w, size=640):
+    """ultralytics-style square letterbox (src/detect/yolo_ultralytics.py:28-35 delegates to it): Python round()."""
+    r = min(size / h, size / w)
+    nw, nh = max(1, int(round(w * r))), max(1, int(round(h * r)))
+    dw, dh = (size - nw) / 2, (size - nh) / 2
+    return nw, nh, int(round(dh - 0.1)), int(round(dw - 0.1))
+
+
+def _resize_tab(ssize, dsize, is_x):
+    scale = 1.0 / (float(dsize) / ssize)
+    o0 = np.zeros(dsize, np.int64); o1 = np.zeros(dsize, np.int64); a = np.zeros((dsize, 2), np.int64)
+    for d in range(dsize):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(np.floor(f)); f = np.float32(f - np.float32(s))
+        if is_x:
+            if s < 0: s, f = 0, np.float32(0)
+            if s >= ssize - 1: s, f = ssize - 1, np.float32(0)
+            o0[d], o1[d] = s, min(s + 1, ssize - 1)
+        else:
+            o0[d], o1[d] = min(max(s, 0), ssize - 1), min(max(s + 1, 0), ssize - 1)
+        a[d, 0] = int(np.rint(np.float32((np.float32(1.0) - f) * np.float32(2048))))
+        a[d, 1] = int(np.rint(np.float32(f * np.float32(2048))))
+    return o0, o1, a
+
+
+def resize_linear_u8(src, dw, dh):
+    """cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR) for 8-bit images (OpenCV resize.cpp: HResizeLinear /
+    VResizeLinear<uchar,int,short>, coefficients scaled by 2048; pinned against cv2 in tests/test_oracle.py)."""
+    H, W = src.shape[:2]
+    x0, x1, xa = _resize_tab(W, dw, True)
+    y0, y1, ya = _resize_tab(H, dh, False)
+    s = src.astype(np.int64)
+    hrow = s[:, x0] * xa[:, 0][None, :, None] + s[:, x1] * xa[:, 1][None, :, None]
+    out = (((ya[:, 0][:, None, None] * (hrow[y0] >> 4)) >> 16) + ((ya[:, 1][:, None, None] * (hrow[y1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def letterbox_f16(img, size=640, pad_value=114):
+    """BGR (H,W,3) uint8 -> (3,size,size) float16: letterbox, BGR->RGB, HWC->CHW, float32(v)/255 rounded to half."""
+    h, w = img.shape[:2]
+    nw, nh, top, left = letterbox_geometry(h, w, size)
+    canvas = np.full((size, size, 3), pad_value, np.uint8)
+    canvas[top:top + nh, left:left + nw] = resize_linear_u8(img, nw, nh) if (nw, nh) != (w, h) else img
+    return (canvas[:, :, ::-1].transpose(2, 0, 1).astype(np.float32) / np.float32(255)).astype(np.float16)

@@ -84,6 +84,10 @@ EXPORTS = {
                                   C.c_int, C.c_double, C.c_int, C.c_int]),
     "rv_median": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
                             C.c_int, C.c_int]),
+    "rv_letterbox_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p]),
+    "rv_letterbox_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "rv_chain_letterbox_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(Params),
+                                         C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "rv_gray_span": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int]),
 }
 
@@ -263,6 +267,44 @@ class Context:
         out = np.empty_like(frames)
         self._ck(self._lib.rv_median(self._h, frames.ctypes.data, out.ctypes.data, n, h, w, 3 * w, 3 * w, int(ksize), MEM_HOST))
         return out
+
+    # -- detector-input stage (letterbox + RGB + CHW + /255 + fp16) ---------------------------
+    @staticmethod
+    def letterbox_geometry(h, w, size=640):
+        """(new_w, new_h, top, left, fused_scale) of the square letterbox; fused_scale > 0 = exact integer down-scale."""
+        v = [C.c_int32() for _ in range(5)]
+        rc = load_library().rv_letterbox_geometry(h, w, size, *[C.byref(x) for x in v])
+        if rc != 0:
+            raise ValueError("bad letterbox geometry arguments")
+        return tuple(x.value for x in v)
+
+    def letterbox_f16(self, frames, size=640, pad_value=114):
+        """BGR frames (N,H,W,3) uint8 -> (N,3,size,size) float16 network input (no chain)."""
+        _check_frames(frames)
+        frames = np.ascontiguousarray(frames)
+        n, h, w, _ = frames.shape
+        out = np.empty((n, 3, size, size), np.float16)
+        self._ck(self._lib.rv_letterbox_f16(self._h, frames.ctypes.data, n, h, w, 3 * w, out.ctypes.data, size, pad_value, MEM_HOST))
+        return out
+
+    def chain_letterbox(self, frames, params, size=640, pad_value=114, want_full=False, out=None):
+        """Chain + detector input in one call: returns (tensor (N,3,size,size) float16, full-res result or None)."""
+        _check_frames(frames)
+        frames = np.ascontiguousarray(frames)
+        n, h, w, _ = frames.shape
+        if out is None:
+            out = np.empty((n, 3, size, size), np.float16)
+        full = np.empty_like(frames) if want_full else None
+        kind = MEM_PINNED if (self.mem_kind(frames) == MEM_PINNED and self.mem_kind(out) == MEM_PINNED and not want_full) else MEM_HOST
+        self._ck(self._lib.rv_chain_letterbox_f16(self._h, frames.ctypes.data, n, h, w, 3 * w, C.byref(params), out.ctypes.data,
+                                                  size, pad_value, full.ctypes.data if want_full else None, 3 * w, kind, None))
+        return out, full
+
+    def chain_letterbox_device(self, in_ptr, out_ptr, n, h, w, params, size=640, pad_value=114, full_ptr=None, stream=None):
+        """Device pointers; asynchronous on `stream` when given."""
+        self._ck(self._lib.rv_chain_letterbox_f16(self._h, C.c_void_p(in_ptr), n, h, w, 3 * w, C.byref(params), C.c_void_p(out_ptr),
+                                                  size, pad_value, C.c_void_p(full_ptr) if full_ptr else None, 3 * w, MEM_DEVICE,
+                                                  C.c_void_p(stream) if stream else None))
 
     def gray_span(self, frames):
         _check_frames(frames)

@@ -9,6 +9,7 @@
 #include "../../include/rv_b200.h"
 
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -45,6 +46,7 @@ struct rv_ctx {
     Buf hist[NPIPE + 1], quads[NPIPE + 1], lut[NPIPE + 1], flags[NPIPE + 1], mm[NPIPE + 1];
     Buf din[NPIPE + 1], dout[NPIPE + 1];
     Buf scratch;                            // stage-level calls
+    Buf lbtab, lbfull;                      // letterbox tables / full-resolution intermediate
     long launches = 0;
     long group_frames = 0, chunk_frames = 0;
     long use_tma = 1;                       // stage k_chain's box with TMA when the source buffer is 16-byte aligned
@@ -292,13 +294,19 @@ int launch_lut(rv_ctx *ctx, const int32_t *hist, const Geo &g, double clip_limit
 }
 
 // one group of frames, everything on device, on stream `st`, using workspace set `ws`
+struct LbFused {            // fused detector-input stage of one group (integer down-scale only)
+    uint16_t *out; int scale, S, top, left, write_full;
+};
+
 int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs, uint8_t *dout, size_t opitch, size_t ofs,
-              int n, int h, int w, const rv_params *p, cudaStream_t st, int32_t **flags_out)
+              int n, int h, int w, const rv_params *p, cudaStream_t st, int32_t **flags_out, const LbFused *lb = nullptr)
 {
     ChainArgs a;
     a.src = din; a.spitch = ipitch; a.sfstride = ifs;
     a.dst = dout; a.dpitch = opitch; a.dfstride = ofs;
     a.quads = nullptr; a.flags = nullptr; a.use_tma = 0;
+    a.lb_out = lb ? lb->out : nullptr; a.lb_scale = lb ? lb->scale : 0; a.lb_S = lb ? lb->S : 0;
+    a.lb_top = lb ? lb->top : 0; a.lb_left = lb ? lb->left : 0; a.write_full = lb ? lb->write_full : 1;
     if (flags_out) *flags_out = nullptr;
     if (!p->clahe) {
         a.g = make_geo(h, w, 2);
@@ -459,6 +467,86 @@ int finish_out(rv_ctx *ctx, Staged &s, void *p, size_t bytes, int mem_kind)
     return RV_OK;
 }
 
+// ---- detector-input stage ------------------------------------------------------------
+struct LbGeo { int S, nw, nh, top, left, scale; };    // scale > 0: exact integer down-scale (fusable)
+
+// ultralytics-style square letterbox: r = min(S/h, S/w); new = round(w r) x round(h r) (Python round = half to even);
+// padding split with the -0.1 / +0.1 rounding so odd remainders put the extra row/column at the bottom/right.
+LbGeo lb_geometry(int h, int w, int S)
+{
+    LbGeo g;
+    g.S = S;
+    const double r = std::min((double)S / h, (double)S / w);
+    g.nw = std::max(1, (int)nearbyint(w * r));
+    g.nh = std::max(1, (int)nearbyint(h * r));
+    const double dw = (S - g.nw) / 2.0, dh = (S - g.nh) / 2.0;
+    g.top = (int)nearbyint(dh - 0.1);
+    g.left = (int)nearbyint(dw - 0.1);
+    g.scale = 0;
+    if (w % g.nw == 0 && h % g.nh == 0 && w / g.nw == h / g.nh) {
+        const int sc = w / g.nw;
+        const bool x_ok = TILE_W % sc == 0;
+        const bool y_ok = (sc & 1) || TILE_H % sc == 0 || (((sc >> 1) - 1) & 1) == 0;
+        if (sc >= 1 && x_ok && y_ok) g.scale = sc;
+    }
+    return g;
+}
+
+// cv2.resize(INTER_LINEAR) tables for 8-bit data (resize.cpp): x clamps with the fraction forced to 0,
+// y keeps the fraction and clips the two row indices; coefficients are cvRound(c * 2048) as shorts.
+void lb_tables(int ssize, int dsize, bool is_x, std::vector<int32_t> &ofs, std::vector<int16_t> &coef)
+{
+    const double scale = 1.0 / ((double)dsize / ssize);
+    ofs.assign(is_x ? dsize : 2 * dsize, 0);
+    coef.assign(2 * dsize, 0);
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int sidx = (int)floorf(f);
+        f -= (float)sidx;
+        if (is_x) {
+            if (sidx < 0) { sidx = 0; f = 0.f; }
+            if (sidx >= ssize - 1) { sidx = ssize - 1; f = 0.f; }
+            ofs[d] = sidx;
+        } else {
+            ofs[2 * d] = std::min(std::max(sidx, 0), ssize - 1);
+            ofs[2 * d + 1] = std::min(std::max(sidx + 1, 0), ssize - 1);
+        }
+        coef[2 * d] = (int16_t)lrintf((1.f - f) * 2048.f);
+        coef[2 * d + 1] = (int16_t)lrintf(f * 2048.f);
+    }
+}
+
+int launch_letterbox(rv_ctx *ctx, const uint8_t *src, size_t pitch, size_t fstride, int n, int h, int w, const LbGeo &g,
+                     int pad, bool only_pad, uint16_t *out, cudaStream_t st)
+{
+    LbArgs a;
+    a.src = src; a.spitch = pitch; a.sfstride = fstride; a.out = out;
+    a.H = h; a.W = w; a.S = g.S; a.nw = g.nw; a.nh = g.nh; a.top = g.top; a.left = g.left; a.pad = pad; a.only_pad = only_pad ? 1 : 0;
+    a.xofs = nullptr; a.xa = nullptr; a.yofs = nullptr; a.ya = nullptr;
+    if (!only_pad) {
+        std::vector<int32_t> xo, yo;
+        std::vector<int16_t> xa, ya;
+        lb_tables(w, g.nw, true, xo, xa);
+        lb_tables(h, g.nh, false, yo, ya);
+        const size_t b0 = xo.size() * 4, b1 = yo.size() * 4, b2 = xa.size() * 2, b3 = ya.size() * 2;
+        RV_TRY(ensure(ctx, ctx->lbtab, b0 + b1 + b2 + b3 + 64));
+        uint8_t *base = (uint8_t *)ctx->lbtab.p;
+        // the tables are tiny; a synchronous copy keeps the host vectors alive for exactly as long as needed
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(base, xo.data(), b0, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(base + b0, yo.data(), b1, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(base + b0 + b1, xa.data(), b2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(base + b0 + b1 + b2, ya.data(), b3, cudaMemcpyHostToDevice));
+        a.xofs = (const int32_t *)base; a.yofs = (const int32_t *)(base + b0);
+        a.xa = (const int16_t *)(base + b0 + b1); a.ya = (const int16_t *)(base + b0 + b1 + b2);
+    }
+    dim3 grid((g.S + 31) / 32, (g.S + 7) / 8, n), block(32, 8);
+    k_letterbox<<<grid, block, 0, st>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return RV_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -515,6 +603,8 @@ void rv_destroy(rv_ctx *ctx)
         for (int i = 0; i <= NPIPE; ++i)
             if (set[i].p) cudaFree(set[i].p);
     if (ctx->scratch.p) cudaFree(ctx->scratch.p);
+    if (ctx->lbtab.p) cudaFree(ctx->lbtab.p);
+    if (ctx->lbfull.p) cudaFree(ctx->lbfull.p);
     for (const TimedLaunch &t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < NPIPE; ++i)
@@ -710,6 +800,83 @@ int rv_median(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w,
     p.space = RV_SPACE_YCRCB; p.grid = 2; p.ksize = ksize; p.clahe = 0;
     if (ksize == 0) return fail(ctx, RV_ERR_ARG, "ksize 0");
     return rv_chain_u8(ctx, in, out, n, h, w, in_pitch, out_pitch, &p, mem_kind, nullptr, nullptr);
+}
+
+int rv_letterbox_geometry(int h, int w, int S, int32_t *new_w, int32_t *new_h, int32_t *top, int32_t *left, int32_t *fused_scale)
+{
+    if (h < 1 || w < 1 || S < 1) return RV_ERR_ARG;
+    const LbGeo g = lb_geometry(h, w, S);
+    if (new_w) *new_w = g.nw;
+    if (new_h) *new_h = g.nh;
+    if (top) *top = g.top;
+    if (left) *left = g.left;
+    if (fused_scale) *fused_scale = g.scale;
+    return RV_OK;
+}
+
+int rv_letterbox_f16(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t pitch, uint16_t *out, int S, int pad_value, int mem_kind)
+{
+    RV_TRY(check_frames(ctx, in, in, n, h, w, pitch, pitch));
+    if (!out || S < 1 || S > 8192 || pad_value < 0 || pad_value > 255) return fail(ctx, RV_ERR_ARG, "bad letterbox arguments");
+    if (n == 0) return RV_OK;
+    CK(cudaSetDevice(ctx->device));
+    const LbGeo g = lb_geometry(h, w, S);
+    const size_t ob = (size_t)n * 3 * S * S * 2;
+    Staged si, so;
+    RV_TRY(stage_in(ctx, si, in, pitch * h * n, mem_kind));
+    RV_TRY(stage_out(ctx, so, out, ob, mem_kind));
+    RV_TRY(launch_letterbox(ctx, (const uint8_t *)si.dev, pitch, pitch * h, n, h, w, g, pad_value, false, (uint16_t *)so.dev, ctx->stream));
+    RV_TRY(finish_out(ctx, so, out, ob, mem_kind));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RV_OK;
+}
+
+int rv_chain_letterbox_f16(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t in_pitch, const rv_params *p,
+                           uint16_t *out, int S, int pad_value, uint8_t *full_out, size_t full_pitch, int mem_kind, void *stream)
+{
+    RV_TRY(check_frames(ctx, in, in, n, h, w, in_pitch, in_pitch));
+    RV_TRY(check_params(ctx, p));
+    if (!p->clahe && p->ksize == 0) return fail(ctx, RV_ERR_ARG, "nothing to do (no CLAHE, no median)");
+    if (p->gate_enable) return fail(ctx, RV_ERR_ARG, "the gate is not supported together with the letterbox stage");
+    if (!out || S < 1 || S > 8192 || pad_value < 0 || pad_value > 255) return fail(ctx, RV_ERR_ARG, "bad letterbox arguments");
+    if (full_out && full_pitch < (size_t)3 * w) return fail(ctx, RV_ERR_ARG, "pitch smaller than 3*w");
+    if (n == 0) return RV_OK;
+    CK(cudaSetDevice(ctx->device));
+    const LbGeo g = lb_geometry(h, w, S);
+    cudaStream_t st = (mem_kind == RV_MEM_DEVICE && stream) ? (cudaStream_t)stream : ctx->stream;
+    const size_t ob = (size_t)n * 3 * S * S * 2, fb = full_pitch * h * n;
+    Staged si, so, sf;
+    RV_TRY(stage_in(ctx, si, in, in_pitch * h * n, mem_kind));
+    RV_TRY(stage_out(ctx, so, out, ob, mem_kind));
+    uint8_t *dfull = nullptr;
+    size_t dpitch = full_pitch;
+    if (full_out) {
+        RV_TRY(stage_out(ctx, sf, full_out, fb, mem_kind));
+        dfull = (uint8_t *)sf.dev;
+    } else if (g.scale == 0) {
+        dpitch = ((size_t)3 * w + 15) & ~(size_t)15;        // unfused: the resize reads a full-resolution intermediate
+        RV_TRY(ensure(ctx, ctx->lbfull, dpitch * h * n));
+        dfull = (uint8_t *)ctx->lbfull.p;
+    }
+    const uint8_t *din = (const uint8_t *)si.dev;
+    if (g.scale > 0) {
+        LbFused lb = {(uint16_t *)so.dev, g.scale, S, g.top, g.left, dfull ? 1 : 0};
+        RV_TRY(launch_letterbox(ctx, din, in_pitch, in_pitch * h, n, h, w, g, pad_value, true, (uint16_t *)so.dev, st));
+        RV_TRY(run_group(ctx, NPIPE, din, in_pitch, in_pitch * h, dfull ? dfull : (uint8_t *)so.dev, dfull ? dpitch : in_pitch,
+                         dfull ? dpitch * h : in_pitch * h, n, h, w, p, st, nullptr, &lb));
+    } else {
+        RV_TRY(run_group(ctx, NPIPE, din, in_pitch, in_pitch * h, dfull, dpitch, dpitch * h, n, h, w, p, st, nullptr, nullptr));
+        RV_TRY(launch_letterbox(ctx, dfull, dpitch, dpitch * h, n, h, w, g, pad_value, false, (uint16_t *)so.dev, st));
+    }
+    if (mem_kind != RV_MEM_DEVICE) {
+        CK(cudaStreamSynchronize(st));
+        RV_TRY(finish_out(ctx, so, out, ob, mem_kind));
+        if (full_out) RV_TRY(finish_out(ctx, sf, full_out, fb, mem_kind));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else if (!stream) {
+        CK(cudaStreamSynchronize(st));
+    }
+    return RV_OK;
 }
 
 int rv_gray_span(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t pitch, int32_t *span, int mem_kind)

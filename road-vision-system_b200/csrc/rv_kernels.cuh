@@ -443,6 +443,10 @@ struct ChainArgs {
     const uint32_t *quads;             // [frames][(grid+1)^2][256]
     const int32_t *flags;              // optional per-frame gate flags (0 = skip frame)
     int use_tma;                       // stage the box with one cp.async.bulk.tensor per CTA (aligned buffers)
+    // optional fused detector-input stage (integer down-scale letterbox, see k_letterbox): 0 = off
+    uint16_t *lb_out;                  // [frames][3][lb_S][lb_S] halves, RGB planes, value/255
+    int lb_scale, lb_S, lb_top, lb_left;
+    int write_full;                    // also store the full-resolution BGR result to dst
 };
 
 template <int K> struct MedianCfg;
@@ -790,7 +794,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
     }
 
     // ---- phase 3: coalesced store of the staging tile (one warp per row, three words per lane)
-    {
+    if (a.write_full) {
         uint8_t *dframe = a.dst + (size_t)f * a.dfstride;
         const int nb = min(3 * TILE_W, 3 * (g.W - x0));          // valid bytes per row
         const bool al4 = ((reinterpret_cast<uintptr_t>(dframe) & 3) == 0) && (a.dpitch % 4 == 0);
@@ -814,6 +818,81 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
                 }
             }
         }
+    }
+    // ---- phase 3b (optional): detector input.  Integer down-scale s: cv2.resize(INTER_LINEAR) degenerates to the
+    // centre pixel (odd s) or the rounded mean of the centre 2x2 block (even s; = the fixed-point formula with both
+    // weights 1024), which never straddles a tile because tile sizes are even and multiples of s are tile aligned in x.
+    if (a.lb_out != nullptr) {
+        const int sc = a.lb_scale, S = a.lb_S;
+        const int off = (sc - 1) >> 1;                           // first source pixel of output d is sc*d + off
+        const int nw = g.W / sc, nh = g.H / sc;
+        const int dx0 = (x0 - off + sc - 1) / sc;                // outputs whose first source column is in this tile
+        const int dx1 = min((x0 + TILE_W - 1 - off) / sc, nw - 1);
+        const int dy0 = (y0 - off + sc - 1) / sc;
+        const int dy1 = min((y0 + TILE_H - 1 - off) / sc, nh - 1);
+        const int ncol = dx1 - dx0 + 1, nrow = dy1 - dy0 + 1;
+        if (ncol > 0 && nrow > 0) {
+            uint16_t *ob = a.lb_out + (size_t)f * 3 * S * S;
+            const bool even = (sc & 1) == 0;
+            for (int i = tid; i < ncol * nrow; i += CHAIN_THREADS) {
+                const int ry = i / ncol, rx = i - ry * ncol;
+                const int dy = dy0 + ry, dx = dx0 + rx;
+                const uint8_t *p = O + (sc * dy + off - y0) * O_STRIDE + 3 * (sc * dx + off - x0);
+                int v[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (even) v[c] = (p[c] + p[c + 3] + p[c + O_STRIDE] + p[c + O_STRIDE + 3] + 2) >> 2;
+                    else v[c] = p[c];
+                }
+                uint16_t *o = ob + (size_t)(a.lb_top + dy) * S + a.lb_left + dx;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)                      // planes are R, G, B; staging is B, G, R
+                    o[(size_t)(2 - c) * S * S] = __half_as_ushort(__float2half_rn(__fdiv_rn((float)v[c], 255.0f)));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Detector-input stage, general form: letterbox to S x S with cv2.resize(INTER_LINEAR) 8-bit
+// fixed-point arithmetic (coefficients scaled by 2048, tables built on the host exactly as OpenCV builds them),
+// constant padding, BGR->RGB, HWC->CHW, /255, fp16.  grid (ceil(S/32), ceil(S/8), frames), block (32, 8).
+// only_pad = 1 writes just the padding (the image rectangle is produced by k_chain's fused phase 3b).
+// ---------------------------------------------------------------------------------------------
+struct LbArgs {
+    const uint8_t *src; size_t spitch, sfstride;
+    uint16_t *out;
+    int H, W, S, nw, nh, top, left, pad, only_pad;
+    const int32_t *xofs;     // [nw] first source column (already clamped)
+    const int16_t *xa;       // [nw][2]
+    const int32_t *yofs;     // [nh][2] both source rows (clamped)
+    const int16_t *ya;       // [nh][2]
+};
+
+__global__ void __launch_bounds__(256) k_letterbox(const LbArgs a)
+{
+    const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
+    if (dx >= a.S || dy >= a.S) return;
+    uint16_t *o = a.out + (size_t)f * 3 * a.S * a.S + (size_t)dy * a.S + dx;
+    const int ix = dx - a.left, iy = dy - a.top;
+    const size_t plane = (size_t)a.S * a.S;
+    if (ix < 0 || ix >= a.nw || iy < 0 || iy >= a.nh) {
+        const uint16_t pv = __half_as_ushort(__float2half_rn(__fdiv_rn((float)a.pad, 255.0f)));
+        o[0] = pv; o[plane] = pv; o[2 * plane] = pv;
+        return;
+    }
+    if (a.only_pad) return;
+    const int sx = a.xofs[ix], sx1 = min(sx + 1, a.W - 1);
+    const int a0 = a.xa[2 * ix], a1 = a.xa[2 * ix + 1];
+    const int b0 = a.ya[2 * iy], b1 = a.ya[2 * iy + 1];
+    const uint8_t *r0 = a.src + (size_t)f * a.sfstride + (size_t)a.yofs[2 * iy] * a.spitch;
+    const uint8_t *r1 = a.src + (size_t)f * a.sfstride + (size_t)a.yofs[2 * iy + 1] * a.spitch;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int h0 = r0[3 * sx + c] * a0 + r0[3 * sx1 + c] * a1;       // horizontal pass, scaled by 2048
+        const int h1 = r1[3 * sx + c] * a0 + r1[3 * sx1 + c] * a1;
+        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;   // VResizeLinear<uchar,int,short>
+        o[(size_t)(2 - c) * plane] = __half_as_ushort(__float2half_rn(__fdiv_rn((float)min(max(v, 0), 255), 255.0f)));
     }
 }
 

@@ -125,3 +125,21 @@ class PreprocessPipeline:
                     np.copyto(out, cur)
                     cur = out
         return cur
+
+    # -- new: chain fused with the detector-input stage ------------------------
+    def process_batch_to_tensor(self, frames: np.ndarray, size: int = 640, pad_value: int = 114, want_frames: bool = False):
+        """(B,H,W,3) uint8 -> ((B,3,size,size) float16 network input, processed frames or None).
+
+        The tensor is what the detector stage builds from `proc` right after the chain (main_preview.py:99 ->
+        yolo_ultralytics.py:28-35: letterbox, BGR->RGB, HWC->CHW, /255, half).  When the chain is the stock
+        CLAHEDehaze -> MedianDerain pair and the down-scale is an exact integer (1080p -> 640), the resize happens inside
+        the chain kernel and the full-resolution frames are only written if `want_frames` is set.
+        """
+        if not isinstance(frames, np.ndarray) or frames.ndim != 4 or frames.shape[3] != 3 or frames.dtype != np.uint8:
+            raise ValueError("frames must be a (B,H,W,3) uint8 numpy array")
+        ctx = self._ctx()
+        segs = self._segments() if (self.enabled and self.ops) else []
+        if self._gate()[0] or len(segs) != 1 or not isinstance(segs[0], Params):
+            proc = self.process_batch(frames)
+            return ctx.letterbox_f16(proc, size, pad_value), (proc if want_frames else None)
+        return ctx.chain_letterbox(frames, segs[0], size, pad_value, want_full=want_frames)

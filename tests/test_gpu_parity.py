@@ -255,3 +255,30 @@ def test_tma_and_plain_staging_agree(ctx):
     assert np.array_equal(a, b)
     for i in range(3):
         assert np.array_equal(a[i], O.chain(frames[i], O.SPACE_YCRCB, 2.0, 8, 5))
+
+
+def test_letterbox_stage_and_fused_chain(ctx):
+    """Detector-input stage: stand-alone letterbox and chain+letterbox, fused (integer scale: 1080p->640 /3,
+    720p /2, 4K-ish /6) and unfused (ragged), all bit-exact in fp16 against the oracle restatement of cv2.resize."""
+    import rvb200
+    from rvb200 import synth
+    rng = np.random.RandomState(6)
+    for (h, w, size) in [(1080, 1920, 640), (720, 1280, 640), (480, 640, 640), (1080, 1923, 640), (123, 457, 320), (300, 200, 640)]:
+        img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        got = ctx.letterbox_f16(img[None], size)[0]
+        assert np.array_equal(got.view(np.uint16), O.letterbox_f16(img, size).view(np.uint16)), (h, w, size)
+        nw, nh, top, left, _ = ctx.letterbox_geometry(h, w, size)
+        assert (nw, nh, top, left) == O.letterbox_geometry(h, w, size)
+    cases = [(1080, 1920, 640, "YCrCb", 8, 5, 3), (720, 1280, 640, "LAB", 8, 3, 2), (1440, 3840, 640, "YCrCb", 16, 3, 6),
+             (1080, 1923, 640, "YCrCb", 8, 3, 0), (480, 640, 640, "YCrCb", 8, 3, 1), (1080, 1920, 640, "YCrCb", 8, 0, 3)]
+    for (h, w, size, space, grid, k, want_scale) in cases:
+        frames = np.stack([synth.road_frame(h, w, 90 + i) for i in range(2)])
+        assert ctx.letterbox_geometry(h, w, size)[4] == want_scale
+        p = rvb200.Params.make(space, 2.0, grid, k)
+        for want_full in (False, True):
+            t, full = ctx.chain_letterbox(frames, p, size, want_full=want_full)
+            for i in range(2):
+                proc = O.chain(frames[i], ospace(space), 2.0, grid, k)
+                assert np.array_equal(t[i].view(np.uint16), O.letterbox_f16(proc, size).view(np.uint16)), (h, w, k, want_full, i)
+                if want_full:
+                    assert np.array_equal(full[i], proc)

@@ -140,3 +140,20 @@ def test_ycrcb_forward_ranges():
     assert Y.min() >= 0 and Y.max() <= 255
     assert cb.min() >= 0 and cb.max() <= 255
     assert cr.min() >= 0 and cr.max() > 255
+
+
+def test_letterbox_restatement_vs_cv2():
+    """resize_linear_u8 / letterbox_f16 restate cv2.resize(INTER_LINEAR) + copyMakeBorder bit for bit (down, up, ragged)."""
+    rng = np.random.RandomState(2)
+    for (h, w, dh, dw) in [(1080, 1920, 360, 640), (720, 1280, 360, 640), (1080, 1923, 359, 640), (123, 457, 172, 640),
+                           (600, 800, 480, 640), (97, 33, 640, 218), (36, 64, 72, 128), (36, 64, 50, 100), (2, 2, 5, 7)]:
+        img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        assert np.array_equal(O.resize_linear_u8(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR)), (h, w, dh, dw)
+    for (h, w, size) in [(1080, 1920, 640), (720, 1280, 640), (480, 640, 640), (1080, 1923, 640), (123, 457, 320), (300, 200, 640), (640, 640, 640)]:
+        img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        a, b = O.letterbox_f16(img, size), R.letterbox_f16(img, size)
+        assert a.dtype == np.float16 and a.shape == (3, size, size)
+        assert np.array_equal(a.view(np.uint16), b.view(np.uint16)), (h, w, size)
+    # the two ways of normalising a byte to half agree for every value: float32(v)/255 -> half  ==  half(v)/half(255)
+    v = np.arange(256)
+    assert np.array_equal((v.astype(np.float32) / np.float32(255)).astype(np.float16), (v.astype(np.float16) / np.float16(255)))

@@ -76,6 +76,35 @@ def main():
             rec["cv2_threads"] = cv2.getNumThreads()
         print(json.dumps(rec), flush=True)
         del d_in, d_out
+    # C5: chain fused with letterbox + fp16 NCHW normalise to 640x640, batch 128 (1080p, YCrCb, k3 = default.yaml chain)
+    from oracle import rv_oracle as O
+    for k, want_full in ((3, False), (3, True), (5, False)):
+        h, w, batch, size = 1080, 1920, 128, 640
+        pool = pools[(h, w)]
+        host = np.stack([pool[i % len(pool)] for i in range(batch)])
+        d_in = torch.from_numpy(host).cuda()
+        d_t = torch.empty((batch, 3, size, size), dtype=torch.float16, device="cuda")
+        d_full = torch.empty_like(d_in) if want_full else None
+        p = rvb200.Params.make("YCrCb", 2.0, 8, k)
+        run = lambda: ctx.chain_letterbox_device(d_in.data_ptr(), d_t.data_ptr(), batch, h, w, p, size, 114,
+                                                 d_full.data_ptr() if want_full else None, stream=st.cuda_stream)
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        want = O.letterbox_f16(O.chain(host[1], O.SPACE_YCRCB, 2.0, 8, k), size)
+        ok = bool(np.array_equal(d_t[1].cpu().numpy().view(np.uint16), want.view(np.uint16)))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            run()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        fps = batch / (ms * 1e-3)
+        algo = 3 * h * w + 3 * size * size * 2 + (3 * h * w if want_full else 0)
+        print(json.dumps({"config": f"C5 1080p chain(k{k})+letterbox 640 fp16 NCHW batch 128" + (" +full-res out" if want_full else ""),
+                          "gpu_fps": round(fps, 1), "ms_per_batch": round(ms, 4), "bit_exact_vs_oracle": ok,
+                          "algorithmic_bytes_per_frame": algo, "hbm_roofline_frac": round(algo * fps / 1e9 / 6533.8, 4)}), flush=True)
+        del d_in, d_t, d_full
 
 
 if __name__ == "__main__":
