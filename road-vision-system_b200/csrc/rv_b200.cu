@@ -47,6 +47,8 @@ struct rv_ctx {
     Buf din[NPIPE + 1], dout[NPIPE + 1];
     Buf scratch;                            // stage-level calls
     Buf lbtab, lbfull;                      // letterbox tables / full-resolution intermediate
+    Buf colp;                               // per-column interpolation records of k_chain
+    int colp_w = -1, colp_tw = -1;
     long launches = 0;
     long group_frames = 0, chunk_frames = 0;
     long use_tma = 1;                       // stage k_chain's box with TMA when the source buffer is 16-byte aligned
@@ -293,6 +295,35 @@ int launch_lut(rv_ctx *ctx, const int32_t *hist, const Geo &g, double clip_limit
     return RV_OK;
 }
 
+// Column records for k_chain (A.3 horizontal terms), rebuilt only when (W, tile width) changes.  Record r describes
+// the four pixels 4*(r-1) .. 4*(r-1)+3 (clamped into the frame): xa, xa1 = 1 - xa, -2^23*xa, -2^23*xa1, quad column.
+// Every value is produced by single IEEE-754 binary32 operations, exactly as the kernel used to compute them.
+int build_colparams(rv_ctx *ctx, const Geo &g, cudaStream_t st)
+{
+    if (ctx->colp_w == g.W && ctx->colp_tw == g.tw && ctx->colp.p) return RV_OK;
+    const int ngroups = (TILE_W / 4) * ((g.W + TILE_W - 1) / TILE_W) + 34;
+    std::vector<float> tab((size_t)ngroups * 20);
+    for (int r = 0; r < ngroups; ++r)
+        for (int j = 0; j < 4; ++j) {
+            const int cx = std::min(std::max(4 * (r - 1) + j, 0), g.W - 1);
+            volatile float t = (float)cx * g.inv_tw;
+            volatile float txf = t - 0.5f;
+            const float fl = floorf(txf);
+            volatile float xa = txf - fl;
+            volatile float xa1 = 1.0f - xa;
+            float *rec = &tab[(size_t)r * 20];
+            rec[j] = xa; rec[4 + j] = xa1; rec[8 + j] = -8388608.0f * xa; rec[12 + j] = -8388608.0f * xa1;
+            const int q = (int)fl + 1;
+            memcpy(&rec[16 + j], &q, 4);
+        }
+    RV_TRY(ensure(ctx, ctx->colp, tab.size() * 4));
+    (void)st;
+    CK(cudaDeviceSynchronize());            // rare path (geometry changed): nothing may still be reading the old table
+    CK(cudaMemcpy(ctx->colp.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    ctx->colp_w = g.W; ctx->colp_tw = g.tw;
+    return RV_OK;
+}
+
 // one group of frames, everything on device, on stream `st`, using workspace set `ws`
 struct LbFused {            // fused detector-input stage of one group (integer down-scale only)
     uint16_t *out; int scale, S, top, left, write_full;
@@ -304,7 +335,7 @@ int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs
     ChainArgs a;
     a.src = din; a.spitch = ipitch; a.sfstride = ifs;
     a.dst = dout; a.dpitch = opitch; a.dfstride = ofs;
-    a.quads = nullptr; a.flags = nullptr; a.use_tma = 0;
+    a.quads = nullptr; a.flags = nullptr; a.use_tma = 0; a.colp = nullptr;
     a.lb_out = lb ? lb->out : nullptr; a.lb_scale = lb ? lb->scale : 0; a.lb_S = lb ? lb->S : 0;
     a.lb_top = lb ? lb->top : 0; a.lb_left = lb ? lb->left : 0; a.write_full = lb ? lb->write_full : 1;
     if (flags_out) *flags_out = nullptr;
@@ -342,6 +373,8 @@ int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs
             a.flags = (int32_t *)ctx->flags[ws].p;
         }
         a.quads = (uint32_t *)ctx->quads[ws].p;
+        RV_TRY(build_colparams(ctx, g, st));
+        a.colp = (const float *)ctx->colp.p;
         RV_TRY(launch_chain(ctx, p->space == RV_SPACE_LAB ? 1 : 0, a, n, p->ksize, st));
     }
     if (a.flags) {
@@ -604,6 +637,7 @@ void rv_destroy(rv_ctx *ctx)
             if (set[i].p) cudaFree(set[i].p);
     if (ctx->scratch.p) cudaFree(ctx->scratch.p);
     if (ctx->lbtab.p) cudaFree(ctx->lbtab.p);
+    if (ctx->colp.p) cudaFree(ctx->colp.p);
     if (ctx->lbfull.p) cudaFree(ctx->lbfull.p);
     for (const TimedLaunch &t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);

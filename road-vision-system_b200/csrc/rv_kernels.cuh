@@ -37,6 +37,9 @@
 #ifndef RV_HIST_DP4A
 #define RV_HIST_DP4A 1
 #endif
+#ifndef RV_MEDIAN5_2ROW
+#define RV_MEDIAN5_2ROW 1
+#endif
 __device__ __forceinline__ void rv_ce_fma(uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi)
 {
     const __half2 x = *reinterpret_cast<const __half2 *>(&a), y = *reinterpret_cast<const __half2 *>(&b);
@@ -443,6 +446,7 @@ struct ChainArgs {
     const uint32_t *quads;             // [frames][(grid+1)^2][256]
     const int32_t *flags;              // optional per-frame gate flags (0 = skip frame)
     int use_tma;                       // stage the box with one cp.async.bulk.tensor per CTA (aligned buffers)
+    const float *colp;                 // per 4-pixel box group: xa[4], xa1[4], -2^23 xa[4], -2^23 xa1[4], quad column[4]
     // optional fused detector-input stage (integer down-scale letterbox, see k_letterbox): 0 = off
     uint16_t *lb_out;                  // [frames][3][lb_S][lb_S] halves, RGB planes, value/255
     int lb_scale, lb_S, lb_top, lb_left;
@@ -554,7 +558,9 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             }
         }
     }
-    // interpolation terms of this lane's four pixels (A.3), evaluated at the clamped coordinate
+    // interpolation terms of this lane's four pixels (A.3), evaluated at the clamped coordinate.  They depend only on
+    // the column, so the host builds them once per (W, tile width) with the same IEEE single-precision operations
+    // (rv_b200.cu: build_colparams) and each lane fetches its five 16-byte records.
     float xa[4], xa1[4], cxa[4], cxa1[4];
     int qxl[4], qcol[4];
     int qx_lo = 0, nqx = 1, qy_lo = 0;
@@ -562,32 +568,35 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
     const bool lane_inside = (x0 - LPAD + 4 * lane >= 0) && (x0 - LPAD + 4 * lane + 3 < g.W);
     if (MODE != 2) {
         auto qof = [](int p, float inv) { return (int)floorf(__fsub_rn(__fmul_rn((float)p, inv), 0.5f)) + 1; };
-        const int cx_first = min(max(x0 - LPAD, 0), g.W - 1), cx_last = min(max(x0 - LPAD + BOX_W - 1, 0), g.W - 1);
         const int cy_first = min(max(y0 - R, 0), g.H - 1), cy_last = min(max(y0 - R + BOX_H - 1, 0), g.H - 1);
-        qx_lo = qof(cx_first, g.inv_tw);
+        const int gbase = (TILE_W / 4) * blockIdx.x;              // record of lane 0 (box group x0/4 - 1, stored at +1)
+        {
+            const float4 *cp = reinterpret_cast<const float4 *>(a.colp) + 5 * (gbase + lane);
+            const float4 r0 = __ldg(cp), r1 = __ldg(cp + 1), r2 = __ldg(cp + 2), r3 = __ldg(cp + 3);
+            const int4 r4 = __ldg(reinterpret_cast<const int4 *>(cp + 4));
+            xa[0] = r0.x; xa[1] = r0.y; xa[2] = r0.z; xa[3] = r0.w;
+            xa1[0] = r1.x; xa1[1] = r1.y; xa1[2] = r1.z; xa1[3] = r1.w;
+            cxa[0] = r2.x; cxa[1] = r2.y; cxa[2] = r2.z; cxa[3] = r2.w;
+            cxa1[0] = r3.x; cxa1[1] = r3.y; cxa1[2] = r3.z; cxa1[3] = r3.w;
+            qxl[0] = r4.x; qxl[1] = r4.y; qxl[2] = r4.z; qxl[3] = r4.w;
+        }
+        qx_lo = __ldg(reinterpret_cast<const int *>(a.colp) + 20 * gbase + 16);
+        nqx = __ldg(reinterpret_cast<const int *>(a.colp) + 20 * (gbase + 31) + 19) - qx_lo + 1;
         qy_lo = qof(cy_first, g.inv_th);
-        nqx = qof(cx_last, g.inv_tw) - qx_lo + 1;
         const int nqy = qof(cy_last, g.inv_th) - qy_lo + 1;
         const int nq = nqx * nqy;
         q_smem = nq <= MAXQ;
         const uint32_t *qf = a.quads + (size_t)f * (g.grid + 1) * (g.grid + 1) * 256;
         if (q_smem) {
-            for (int i = tid; i < nq * 256; i += CHAIN_THREADS) {
-                const int lq = i >> 8, v = i & 255;
+            for (int i = tid; i < nq * 64; i += CHAIN_THREADS) {   // 64 x 16 bytes per quad table
+                const int lq = i >> 6, v4 = i & 63;
                 const int qy = qy_lo + lq / nqx, qx = qx_lo + lq % nqx;
-                Qs[i] = __ldg(qf + ((size_t)qy * (g.grid + 1) + qx) * 256 + v);
+                reinterpret_cast<uint4 *>(Qs)[i] = __ldg(reinterpret_cast<const uint4 *>(qf + ((size_t)qy * (g.grid + 1) + qx) * 256) + v4);
             }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int cx = min(max(x0 - LPAD + 4 * lane + j, 0), g.W - 1);
-            const float txf = __fsub_rn(__fmul_rn((float)cx, g.inv_tw), 0.5f);
-            const float fl = floorf(txf);
-            xa[j] = __fsub_rn(txf, fl);
-            xa1[j] = __fsub_rn(1.0f, xa[j]);
-            cxa[j] = -8388608.0f * xa[j];        // exact (power-of-two scale)
-            cxa1[j] = -8388608.0f * xa1[j];
-            qxl[j] = (int)fl + 1 - qx_lo;
+            qxl[j] -= qx_lo;
             qcol[j] = qxl[j] << 8;
         }
         for (int ry = tid; ry < BOX_H; ry += CHAIN_THREADS) {
@@ -737,6 +746,46 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
     __syncthreads();
 
     // ---- phase 2: k x k median per channel plane; lanes of each u16x2 are output rows (s, s+HALF)
+#if RV_MEDIAN5_2ROW
+    if constexpr (K == 5) {
+        // two vertically adjacent output rows per task (slots s, s+1): the four middle window rows are shared
+        constexpr int NSLOT = S::NSLOT;
+        constexpr int M = RV_MEDIAN5X2_M;
+        constexpr int NG = TILE_W / M;
+        constexpr int NC = M + 4;
+        static_assert(M == 4 && TILE_W % M == 0 && HALF % 2 == 0, "two-row median layout");
+        for (int task = tid; task < 3 * NG * (HALF / 2); task += CHAIN_THREADS) {
+            const int m = task % NG;
+            const int t2 = task / NG;
+            const int c = t2 % 3, s = 2 * (t2 / 3);
+            if (x0 + M * m >= g.W) continue;
+            if (y0 + s >= g.H) continue;
+            uint32_t v[NC][6];
+            const uint32_t *pc = P + (c * NSLOT + s) * P_STRIDE;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) {
+                const uint4 *p4 = reinterpret_cast<const uint4 *>(pc + d * P_STRIDE + 4 * m);
+                const uint4 q0 = p4[0], q1 = p4[1], q2 = p4[2];
+                const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+                for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[LPAD - R + cc];
+            }
+            uint32_t out[2][M];
+            rv_median5x2_net(v, out);
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                uint8_t *o0 = O + (s + hrow) * O_STRIDE + 3 * M * m + c;
+                uint8_t *o1 = o0 + HALF * O_STRIDE;
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    o0[3 * j] = (uint8_t)(out[hrow][j] & 255);
+                    o1[3 * j] = (uint8_t)((out[hrow][j] >> 16) & 255);
+                }
+            }
+        }
+        __syncthreads();
+    } else
+#endif
     if constexpr (K > 0) {
         constexpr int NSLOT = S::NSLOT;
         constexpr int M = MedianCfg<K>::M;
