@@ -20,6 +20,8 @@
 
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "rv_lab_tables.h"
 
 // Median compare-exchange forms.  Plane values are kept as 0x6400|v per 16-bit lane: as unsigned
@@ -619,6 +621,10 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
     // packed u16x2 plane words (two values per VIMNMX.S16x2) instead of per value; LAB / passthrough values are exact.
     constexpr bool RAW = (MODE == 0) && (K > 0);
     constexpr int OB = RAW ? 0x6400 : 0;
+    // phase 1 is instantiated twice (quad tables in shared memory / fetched from global) and the CTA-uniform choice is
+    // made once, outside: a predicated dual path costs issue slots for every masked-off address instruction.
+    auto phase1 = [&](auto QS) {
+    constexpr bool q_in_smem = decltype(QS)::value;
     auto compute_row = [&](int ry, int (&o)[12]) {
         int Bv[4], Gv[4], Rv[4];
         float4 rp;
@@ -629,19 +635,24 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             rp = rowp[ry];
             ar = A + __float_as_int(rp.w);                 // staged row of the clamped image row
         }
+        uint32_t px[4];                                    // (B, G, R, x) of each pixel in one word
         if (lane_inside) {
             const uint32_t *p = reinterpret_cast<const uint32_t *>(ar + aoff + 12 * lane);
             const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
-            Bv[0] = w0 & 255; Gv[0] = (w0 >> 8) & 255; Rv[0] = (w0 >> 16) & 255;
-            Bv[1] = w0 >> 24; Gv[1] = w1 & 255; Rv[1] = (w1 >> 8) & 255;
-            Bv[2] = (w1 >> 16) & 255; Gv[2] = w1 >> 24; Rv[2] = w2 & 255;
-            Bv[3] = (w2 >> 8) & 255; Gv[3] = (w2 >> 16) & 255; Rv[3] = w2 >> 24;
+            px[0] = w0; px[1] = __funnelshift_r(w0, w1, 24); px[2] = __funnelshift_r(w1, w2, 16); px[3] = w2 >> 8;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                Bv[j] = px[j] & 255;
+                Gv[j] = __byte_perm(px[j], 0, 0x4441);
+                Rv[j] = __byte_perm(px[j], 0, 0x4442);
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int cx = min(max(x0 - LPAD + 4 * lane + j, 0), g.W - 1);
                 const uint8_t *p = ar + aoff + 3 * (cx - (x0 - LPAD));
                 Bv[j] = p[0]; Gv[j] = p[1]; Rv[j] = p[2];
+                px[j] = (uint32_t)Bv[j] | ((uint32_t)Gv[j] << 8) | ((uint32_t)Rv[j] << 16);
             }
         }
         if (MODE == 2) {
@@ -659,12 +670,14 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             } else {
                 // A.1 forward.  Over all 2^24 colours Cb never leaves [1,255] and Cr never goes below 0
                 // (tests/test_oracle.py::test_ycrcb_forward_ranges), so only Cr's upper bound needs a clamp.
-                L = (4899 * Rv[j] + 9617 * Gv[j] + 1868 * Bv[j] + 8192) >> 14;
+                // Y = (4899 R + 9617 G + 1868 B + 8192) >> 14 as two byte dot products on the packed pixel word
+                constexpr uint32_t LO = 76u | (145u << 8) | (35u << 16), HI = 7u | (37u << 8) | (19u << 16);
+                L = (int)((__dp4a(px[j], LO, 8192u) + (__dp4a(px[j], HI, 0u) << 8)) >> 14);
                 c1 = min(((Rv[j] - L) * 11682 + ((128 << 14) + 8192)) >> 14, 255);
                 c2 = ((Bv[j] - L) * 9241 + ((128 << 14) + 8192)) >> 14;
             }
             uint32_t q;
-            if (q_smem) q = Qs[qrow + qcol[j] + L];
+            if constexpr (q_in_smem) q = Qs[qrow + qcol[j] + L];
             else q = __ldg(qglob + (((size_t)qrow * (g.grid + 1) + (qxl[j] + qx_lo)) << 8) + L);
             // 0x4B0000vv = 2^23 + vv ; fma(2^23 + v, w, -2^23 * w) == v * w rounded once (A.3: no FMA contraction
             // between the products and the sums -- each step below is individually rounded)
@@ -743,6 +756,8 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             }
         }
     }
+    };   // phase1
+    if (q_smem) phase1(std::true_type{}); else phase1(std::false_type{});
     __syncthreads();
 
     // ---- phase 2: k x k median per channel plane; lanes of each u16x2 are output rows (s, s+HALF)
@@ -753,7 +768,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
         constexpr int M = RV_MEDIAN5X2_M;
         constexpr int NG = TILE_W / M;
         constexpr int NC = M + 4;
-        static_assert(M == 4 && TILE_W % M == 0 && HALF % 2 == 0, "two-row median layout");
+        static_assert((M == 4 || M == 6) && TILE_W % M == 0 && HALF % 2 == 0, "two-row median layout");
         for (int task = tid; task < 3 * NG * (HALF / 2); task += CHAIN_THREADS) {
             const int m = task % NG;
             const int t2 = task / NG;
@@ -762,13 +777,25 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             if (y0 + s >= g.H) continue;
             uint32_t v[NC][6];
             const uint32_t *pc = P + (c * NSLOT + s) * P_STRIDE;
+            if constexpr (M == 4) {
 #pragma unroll
-            for (int d = 0; d < 6; ++d) {
-                const uint4 *p4 = reinterpret_cast<const uint4 *>(pc + d * P_STRIDE + 4 * m);
-                const uint4 q0 = p4[0], q1 = p4[1], q2 = p4[2];
-                const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+                for (int d = 0; d < 6; ++d) {
+                    const uint4 *p4 = reinterpret_cast<const uint4 *>(pc + d * P_STRIDE + 4 * m);
+                    const uint4 q0 = p4[0], q1 = p4[1], q2 = p4[2];
+                    const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
-                for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[LPAD - R + cc];
+                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[LPAD - R + cc];
+                }
+            } else {
+#pragma unroll
+                for (int d = 0; d < 6; ++d) {
+                    const uint2 *p2 = reinterpret_cast<const uint2 *>(pc + d * P_STRIDE + M * m + LPAD - R);
+#pragma unroll
+                    for (int cc = 0; cc < NC / 2; ++cc) {
+                        const uint2 q = p2[cc];
+                        v[2 * cc][d] = q.x; v[2 * cc + 1][d] = q.y;
+                    }
+                }
             }
             uint32_t out[2][M];
             rv_median5x2_net(v, out);

@@ -517,7 +517,7 @@ def main():
                 z = "skipped"
             emit(d, inputs, outs, k, M, fh)
             print(f"k={k} M={M} strategy={strat}: {nops} ops ({nops / M:.1f}/output), zero-one={z}")
-        M2 = int(os.environ.get("RV_MEDIAN5X2_M", "4"))
+        M2 = int(os.environ.get("RV_MEDIAN5X2_M", "6"))
         best = None
         for parity in (0, 1):
             for rpar in (0, 1):
