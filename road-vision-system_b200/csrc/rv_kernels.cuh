@@ -620,7 +620,6 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
     // YCrCb results are produced UNCLAMPED with RV_BIAS16 added (K > 0): the saturation to [0,255] happens on the
     // packed u16x2 plane words (two values per VIMNMX.S16x2) instead of per value; LAB / passthrough values are exact.
     constexpr bool RAW = (MODE == 0) && (K > 0);
-    constexpr int OB = RAW ? 0x6400 : 0;
     // phase 1 is instantiated twice (quad tables in shared memory / fetched from global) and the CTA-uniform choice is
     // made once, outside: a predicated dual path costs issue slots for every masked-off address instruction.
     auto phase1 = [&](auto QS) {
@@ -693,14 +692,17 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             const float bot = __fmul_rn(__fadd_rn(p10, p11), ya);
             const float res = __fadd_rn(top, bot);
             // round-half-even via the 1.5*2^23 trick; res <= 255*(1 + 1e-6), so the result is already in [0,255]
-            const int L2 = __float_as_int(__fadd_rn(res, 12582912.0f)) & 0x1FF;
+            // RAW: the bias 0x6400 rides along in the magic constant and the float's upper bits are left in place; only the
+            // low 16 bits of the sums below are ever used (pack2 keeps the low halves), so no masking is needed.
+            const int L2 = RAW ? __float_as_int(__fadd_rn(res, 12582912.0f + 25600.0f))
+                               : (__float_as_int(__fadd_rn(res, 12582912.0f)) & 0x1FF);
             if (MODE == 1) {
                 lab_inv(tabs, L2, c1, c2, o[j], o[4 + j], o[8 + j]);
             } else {
                 // A.1 inverse with the -128 offsets folded into the rounding constants
-                const int bb = L2 + OB + ((c2 * 29049 + (8192 - 128 * 29049)) >> 14);
-                const int gg = L2 + OB + ((c2 * -5636 + c1 * -11698 + (8192 + 128 * (5636 + 11698))) >> 14);
-                const int rr = L2 + OB + ((c1 * 22987 + (8192 - 128 * 22987)) >> 14);
+                const int bb = L2 + ((c2 * 29049 + (8192 - 128 * 29049)) >> 14);
+                const int gg = L2 + ((c2 * -5636 + c1 * -11698 + (8192 + 128 * (5636 + 11698))) >> 14);
+                const int rr = L2 + ((c1 * 22987 + (8192 - 128 * 22987)) >> 14);
                 if (RAW) { o[j] = bb; o[4 + j] = gg; o[8 + j] = rr; }
                 else { o[j] = sat8(bb); o[4 + j] = sat8(gg); o[8 + j] = sat8(rr); }
             }
