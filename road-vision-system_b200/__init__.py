@@ -15,10 +15,10 @@ from .preprocess import PreprocessPipeline
 from .preprocess.base import PreprocessOp
 from .preprocess.registry import REGISTRY, get_op_class
 from .preprocess.ops import CLAHEDehaze, MedianDerain
-from .io_video import VideoSource, Frame, FPSMeter
+from .io_video import VideoSource, Frame, FPSMeter, BatchFeeder, SyntheticReader
 
 __all__ = [
     "Context", "Params", "RvError", "default_context", "library_path", "build_library",
     "PreprocessPipeline", "PreprocessOp", "REGISTRY", "get_op_class",
-    "CLAHEDehaze", "MedianDerain", "VideoSource", "Frame", "FPSMeter",
+    "CLAHEDehaze", "MedianDerain", "VideoSource", "Frame", "FPSMeter", "BatchFeeder", "SyntheticReader",
 ]

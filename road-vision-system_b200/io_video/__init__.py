@@ -1,4 +1,5 @@
-from .capture import Frame, VideoSource
+from .capture import Frame, SyntheticReader, VideoSource
+from .feeder import Batch, BatchFeeder
 from .fps_meter import FPSMeter
 
-__all__ = ["VideoSource", "Frame", "FPSMeter"]
+__all__ = ["VideoSource", "Frame", "FPSMeter", "SyntheticReader", "BatchFeeder", "Batch"]

@@ -132,3 +132,21 @@ def test_shard_plan_and_gloo_world2(tmp_path):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                            "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)], env=env, timeout=300)
+
+
+def test_batch_feeder_order_timestamps_backpressure():
+    import rvb200
+    from rvb200.io_video.capture import SyntheticReader
+    pool = [np.full((4, 6, 3), i, np.uint8) for i in range(5)]
+    vs = rvb200.VideoSource(reader=SyntheticReader(pool, limit=23))
+    feeder = rvb200.BatchFeeder(vs, batch=4, shape=(4, 6, 3), depth=2)
+    seen, held = [], []
+    for b in feeder:
+        assert b.frames.shape == (b.count, 4, 6, 3) and len(b.ts) == b.count and np.all(np.diff(b.ts) >= 0)
+        seen.extend(int(f[0, 0, 0]) for f in b.frames)
+        held.append(b)
+        if len(held) == 2:                 # the reader is blocked now (depth 2): release both and go on
+            for h in held:
+                feeder.release(h)
+            held = []
+    assert seen == [i % 5 for i in range(23)]          # nothing dropped, nothing reordered, partial last batch delivered
