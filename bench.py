@@ -179,10 +179,10 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     pool = make_pool()
-    sample = 16                                   # frames per step
-    frames = [pool[i % POOL] for i in range(sample)]
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
+    sample = min(max(16, 2 * cores), 4 * BATCH)   # frames per step: two per worker so every host core stays busy
+    frames = [pool[i % POOL] for i in range(sample)]
     with mp.get_context("fork").Pool(cores) as pp:
         chunks = [[f for f in frames[c::cores]] for c in range(cores)]
         chunks = [c for c in chunks if c]
