@@ -43,8 +43,12 @@ struct rv_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;          // main stream (device buffers, stage-level calls)
     cudaStream_t pipe[NPIPE] = {};          // H2D / compute / D2H pipeline for host buffers
-    Buf hist[NPIPE + 1], quads[NPIPE + 1], lut[NPIPE + 1], flags[NPIPE + 1], mm[NPIPE + 1];
-    Buf din[NPIPE + 1], dout[NPIPE + 1];
+    Buf hist[NPIPE + 2], quads[NPIPE + 2], lut[NPIPE + 2], flags[NPIPE + 2], mm[NPIPE + 2];   // [NPIPE], [NPIPE+1]: device path
+    Buf din[NPIPE + 2], dout[NPIPE + 2];
+    cudaStream_t aux = nullptr;             // high-priority stream: histogram/LUT of the next group under the current k_chain
+    cudaEvent_t ev_entry = nullptr, ev_pre[2] = {}, ev_chain[2] = {};
+    long overlap_groups = 0;                // device path: split a batch into this many groups (0/1 = no overlap); measured
+                                            // slower on B200 (k_chain leaves no SM resources for co-resident CTAs), kept as an option
     Buf scratch;                            // stage-level calls
     Buf lbtab, lbfull;                      // letterbox tables / full-resolution intermediate
     Buf colp;                               // per-column interpolation records of k_chain
@@ -330,8 +334,11 @@ struct LbFused {            // fused detector-input stage of one group (integer 
 };
 
 int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs, uint8_t *dout, size_t opitch, size_t ofs,
-              int n, int h, int w, const rv_params *p, cudaStream_t st, int32_t **flags_out, const LbFused *lb = nullptr)
+              int n, int h, int w, const rv_params *p, cudaStream_t st, int32_t **flags_out, const LbFused *lb = nullptr,
+              cudaStream_t st_pre = nullptr, cudaEvent_t ev_pre = nullptr)
 {
+    // st_pre (optional): histogram / LUT / gate flags run there and `st` waits for them before k_chain
+    cudaStream_t sp = st_pre ? st_pre : st;
     ChainArgs a;
     a.src = din; a.spitch = ipitch; a.sfstride = ifs;
     a.dst = dout; a.dpitch = opitch; a.dfstride = ofs;
@@ -347,8 +354,8 @@ int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs
             RV_TRY(ensure(ctx, ctx->mm[ws], (size_t)n * 8));
             RV_TRY(ensure(ctx, ctx->flags[ws], (size_t)n * 4));
             RV_TRY(launch_hist(ctx, din, ipitch, ifs, a.g, RV_SPACE_YCRCB, n, (int32_t *)ctx->hist[ws].p, nullptr,
-                               (int32_t *)ctx->mm[ws].p, st));
-            k_gate_flags<<<(n + 127) / 128, 128, 0, st>>>((int32_t *)ctx->mm[ws].p, n, (float)p->gate_thresh, (int32_t *)ctx->flags[ws].p);
+                               (int32_t *)ctx->mm[ws].p, sp));
+            k_gate_flags<<<(n + 127) / 128, 128, 0, sp>>>((int32_t *)ctx->mm[ws].p, n, (float)p->gate_thresh, (int32_t *)ctx->flags[ws].p);
             ctx->launches++;
             a.flags = (int32_t *)ctx->flags[ws].p;
         }
@@ -365,14 +372,18 @@ int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs
             RV_TRY(ensure(ctx, ctx->flags[ws], (size_t)n * 4));
             mm = (int32_t *)ctx->mm[ws].p;
         }
-        RV_TRY(launch_hist(ctx, din, ipitch, ifs, g, p->space, n, (int32_t *)ctx->hist[ws].p, nullptr, mm, st));
-        RV_TRY(launch_lut(ctx, (int32_t *)ctx->hist[ws].p, g, p->clip_limit, n, nullptr, (uint32_t *)ctx->quads[ws].p, st));
+        RV_TRY(launch_hist(ctx, din, ipitch, ifs, g, p->space, n, (int32_t *)ctx->hist[ws].p, nullptr, mm, sp));
+        RV_TRY(launch_lut(ctx, (int32_t *)ctx->hist[ws].p, g, p->clip_limit, n, nullptr, (uint32_t *)ctx->quads[ws].p, sp));
         if (p->gate_enable) {
-            k_gate_flags<<<(n + 127) / 128, 128, 0, st>>>(mm, n, (float)p->gate_thresh, (int32_t *)ctx->flags[ws].p);
+            k_gate_flags<<<(n + 127) / 128, 128, 0, sp>>>(mm, n, (float)p->gate_thresh, (int32_t *)ctx->flags[ws].p);
             ctx->launches++;
             a.flags = (int32_t *)ctx->flags[ws].p;
         }
         a.quads = (uint32_t *)ctx->quads[ws].p;
+        if (st_pre) {
+            CK(cudaEventRecord(ev_pre, st_pre));
+            CK(cudaStreamWaitEvent(st, ev_pre, 0));
+        }
         RV_TRY(build_colparams(ctx, g, st));
         a.colp = (const float *)ctx->colp.p;
         RV_TRY(launch_chain(ctx, p->space == RV_SPACE_LAB ? 1 : 0, a, n, p->ksize, st));
@@ -406,8 +417,29 @@ long auto_chunk(const rv_ctx *ctx, int h, int w)
 int chain_device(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w, size_t ipitch, size_t opitch,
                  const rv_params *p, int32_t *processed_host, cudaStream_t st)
 {
-    const long G = auto_group(ctx, h, w);
     const size_t ifs = ipitch * h, ofs = opitch * h;
+    // Overlap: the batch is cut into a few groups; histogram + LUT of group i+1 run on a high-priority side stream while
+    // k_chain of group i (instruction bound, memory system idle) owns the SMs.  Two workspace sets alternate.
+    const bool overlap = ctx->overlap_groups > 1 && p->clahe && !p->gate_enable && !processed_host && n >= 2 * ctx->overlap_groups &&
+                         ctx->group_frames == 0;
+    if (overlap) {
+        const int ng = (int)ctx->overlap_groups;
+        const int per = (n + ng - 1) / ng;
+        RV_TRY(build_colparams(ctx, make_geo(h, w, p->grid), st));      // before any asynchronous work is queued
+        CK(cudaEventRecord(ctx->ev_entry, st));
+        CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_entry, 0));
+        int gi = 0;
+        for (int f0 = 0; f0 < n; f0 += per, ++gi) {
+            const int g = std::min(per, n - f0);
+            const int ws = NPIPE + (gi & 1);
+            if (gi >= 2) CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_chain[gi & 1], 0));      // workspace `ws` free again
+            RV_TRY(run_group(ctx, ws, in + (size_t)f0 * ifs, ipitch, ifs, out + (size_t)f0 * ofs, opitch, ofs, g, h, w, p, st, nullptr,
+                             nullptr, ctx->aux, ctx->ev_pre[gi & 1]));
+            CK(cudaEventRecord(ctx->ev_chain[gi & 1], st));
+        }
+        return RV_OK;
+    }
+    const long G = auto_group(ctx, h, w);
     for (int f0 = 0; f0 < n; f0 += (int)G) {
         const int g = (int)std::min<long>(G, n - f0);
         int32_t *flags = nullptr;
@@ -464,6 +496,7 @@ int wait_all(rv_ctx *ctx)
 {
     for (int i = 0; i < NPIPE; ++i) CK(cudaStreamSynchronize(ctx->pipe[i]));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->aux));
     return RV_OK;
 }
 
@@ -610,6 +643,14 @@ int rv_create(int device, rv_ctx **out)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
     for (int i = 0; i < NPIPE; ++i)
         if (cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, hi) != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
+        cudaEvent_t *evs[] = {&ctx->ev_entry, &ctx->ev_pre[0], &ctx->ev_pre[1], &ctx->ev_chain[0], &ctx->ev_chain[1]};
+        for (cudaEvent_t *e : evs)
+            if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
+    }
     // LAB tables
     LabTabs *t = new (std::nothrow) LabTabs();
     if (!t) { delete ctx; return RV_ERR_NOMEM; }
@@ -633,7 +674,7 @@ void rv_destroy(rv_ctx *ctx)
     cudaDeviceSynchronize();
     Buf *sets[] = {ctx->hist, ctx->quads, ctx->lut, ctx->flags, ctx->mm, ctx->din, ctx->dout};
     for (Buf *set : sets)
-        for (int i = 0; i <= NPIPE; ++i)
+        for (int i = 0; i <= NPIPE + 1; ++i)
             if (set[i].p) cudaFree(set[i].p);
     if (ctx->scratch.p) cudaFree(ctx->scratch.p);
     if (ctx->lbtab.p) cudaFree(ctx->lbtab.p);
@@ -644,6 +685,10 @@ void rv_destroy(rv_ctx *ctx)
     for (int i = 0; i < NPIPE; ++i)
         if (ctx->pipe[i]) cudaStreamDestroy(ctx->pipe[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
+    cudaEvent_t evs[] = {ctx->ev_entry, ctx->ev_pre[0], ctx->ev_pre[1], ctx->ev_chain[0], ctx->ev_chain[1]};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -656,6 +701,7 @@ int rv_set_option(rv_ctx *ctx, const char *name, long value)
     if (strcmp(name, "chunk_frames") == 0) { ctx->chunk_frames = value; return RV_OK; }
     if (strcmp(name, "kernel_timing") == 0) { ctx->kernel_timing = value; return RV_OK; }
     if (strcmp(name, "use_tma") == 0) { ctx->use_tma = value; return RV_OK; }
+    if (strcmp(name, "overlap_groups") == 0) { ctx->overlap_groups = value; return RV_OK; }
     return fail(ctx, RV_ERR_ARG, "unknown option '%s'", name);
 }
 
