@@ -115,9 +115,10 @@ __device__ __forceinline__ void lab_fwd(const LabTabs *t, int B, int G, int R, i
     const int fX = t->cb[(1777 * r + 1541 * g + 778 * b + 2048) >> 12];
     const int fY = t->cb[(871 * r + 2929 * g + 296 * b + 2048) >> 12];
     const int fZ = t->cb[(73 * r + 448 * g + 3575 * b + 2048) >> 12];
+    // over all 2^24 colours a stays in [42,226] and b in [20,223] (tests/test_oracle.py::test_lab_forward_ranges): no saturation needed
     L = (296 * fY - 1336934 + 16384) >> 15;
-    a = sat8((500 * (fX - fY) + ((128 << 15) + 16384)) >> 15);
-    bb = sat8((200 * (fY - fZ) + ((128 << 15) + 16384)) >> 15);
+    a = (500 * (fX - fY) + ((128 << 15) + 16384)) >> 15;
+    bb = (200 * (fY - fZ) + ((128 << 15) + 16384)) >> 15;
 }
 __device__ __forceinline__ int lab_xz(int i)
 {
@@ -125,14 +126,22 @@ __device__ __forceinline__ int lab_xz(int i)
     const int cub = (((i * i) >> 14) * i) >> 14;
     return i <= 3390 ? lin : cub;
 }
-// A.2 inverse
-__device__ __forceinline__ void lab_inv(const LabTabs *t, int L, int a, int b, int &B, int &G, int &R)
+// A.2 inverse.  lab_inv_args gives the two XZ arguments; when every argument in the warp is above 3390 (any pixel that is not
+// nearly black) the caller uses CUBIC_ONLY = true and the linear branch of XZ with its division is never evaluated.
+__device__ __forceinline__ void lab_inv_args(const LabTabs *t, int L, int a, int b, int &y, int &ix, int &iz)
 {
-    const int y = t->yt[L], fy = t->ft[L];
+    y = t->yt[L];
+    const int fy = t->ft[L];
     const int adiv = ((5 * a * 53687 + 128) >> 13) - 4194;
     const int bdiv = ((b * 41943 + 16) >> 9) - 10485 + 1;
-    const int x = lab_xz(fy + adiv);
-    const int z = lab_xz(fy - bdiv);
+    ix = fy + adiv;
+    iz = fy - bdiv;
+}
+template <bool CUBIC_ONLY>
+__device__ __forceinline__ void lab_inv_tail(const LabTabs *t, int y, int ix, int iz, int &B, int &G, int &R)
+{
+    const int x = CUBIC_ONLY ? ((((ix * ix) >> 14) * ix) >> 14) : lab_xz(ix);
+    const int z = CUBIC_ONLY ? ((((iz * iz) >> 14) * iz) >> 14) : lab_xz(iz);
     int ro = (12615 * x - 6296 * y - 2223 * z + 8192) >> 14;
     int go = (-3773 * x + 7684 * y + 185 * z + 8192) >> 14;
     int bo = (217 * x - 836 * y + 4715 * z + 8192) >> 14;
@@ -660,6 +669,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             return;
         }
         const float ya = rp.x, ya1 = rp.y;
+        int ly[4], lx[4], lz[4];                                 // LAB: y and the two XZ arguments of the four pixels
         const int qrow = __float_as_int(rp.z);                    // (local quad row * quads per row) << 8, or the global row
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -697,7 +707,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             const int L2 = RAW ? __float_as_int(__fadd_rn(res, 12582912.0f + 25600.0f))
                                : (__float_as_int(__fadd_rn(res, 12582912.0f)) & 0x1FF);
             if (MODE == 1) {
-                lab_inv(tabs, L2, c1, c2, o[j], o[4 + j], o[8 + j]);
+                lab_inv_args(tabs, L2, c1, c2, ly[j], lx[j], lz[j]);
             } else {
                 // A.1 inverse with the -128 offsets folded into the rounding constants
                 const int bb = L2 + ((c2 * 29049 + (8192 - 128 * 29049)) >> 14);
@@ -705,6 +715,16 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
                 const int rr = L2 + ((c1 * 22987 + (8192 - 128 * 22987)) >> 14);
                 if (RAW) { o[j] = bb; o[4 + j] = gg; o[8 + j] = rr; }
                 else { o[j] = sat8(bb); o[4 + j] = sat8(gg); o[8 + j] = sat8(rr); }
+            }
+        }
+        if (MODE == 1) {
+            const int lowest = min(min(min(lx[0], lz[0]), min(lx[1], lz[1])), min(min(lx[2], lz[2]), min(lx[3], lz[3])));
+            if (__any_sync(0xffffffffu, lowest <= 3390)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) lab_inv_tail<false>(tabs, ly[j], lx[j], lz[j], o[j], o[4 + j], o[8 + j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) lab_inv_tail<true>(tabs, ly[j], lx[j], lz[j], o[j], o[4 + j], o[8 + j]);
             }
         }
     };
@@ -719,9 +739,9 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
         // no median: write the interleaved result straight to the staging tile (lanes 0 and 31 hold halo only)
         for (int ry = warp; ry < TILE_H; ry += CHAIN_WARPS) {
             if (y0 + ry >= g.H) break;
+            int o[12];
+            compute_row(ry, o);                      // all 32 lanes: compute_row votes across the warp (LAB inverse)
             if (lane >= 1 && lane <= 30) {
-                int o[12];
-                compute_row(ry, o);
                 uint32_t *op = reinterpret_cast<uint32_t *>(O + ry * O_STRIDE + 12 * (lane - 1));
                 op[0] = (uint32_t)o[0] | ((uint32_t)o[4] << 8) | ((uint32_t)o[8] << 16) | ((uint32_t)o[1] << 24);
                 op[1] = (uint32_t)o[5] | ((uint32_t)o[9] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[6] << 24);

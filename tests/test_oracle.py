@@ -157,3 +157,18 @@ def test_letterbox_restatement_vs_cv2():
     # the two ways of normalising a byte to half agree for every value: float32(v)/255 -> half  ==  half(v)/half(255)
     v = np.arange(256)
     assert np.array_equal((v.astype(np.float32) / np.float32(255)).astype(np.float16), (v.astype(np.float16) / np.float16(255)))
+
+
+def test_lab_forward_ranges():
+    """The CUDA kernel does not saturate the forward a/b channels: over all 2^24 colours they stay well inside [0,255]."""
+    from oracle.gen_lab_tables import build_tables
+    t = build_tables()
+    G8, CB = t["G8"].astype(np.int64), t["CB"].astype(np.int64)
+    v = np.arange(1 << 24, dtype=np.int64)
+    B, G, R = G8[v & 255], G8[(v >> 8) & 255], G8[v >> 16]
+    fX = CB[(1777 * R + 1541 * G + 778 * B + 2048) >> 12]
+    fY = CB[(871 * R + 2929 * G + 296 * B + 2048) >> 12]
+    fZ = CB[(73 * R + 448 * G + 3575 * B + 2048) >> 12]
+    a = (500 * (fX - fY) + (128 << 15) + 16384) >> 15
+    b = (200 * (fY - fZ) + (128 << 15) + 16384) >> 15
+    assert (a.min(), a.max(), b.min(), b.max()) == (42, 226, 20, 223)

@@ -1,5 +1,5 @@
 #!/bin/bash
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
 for o in 0 2 4 8; do
   echo "overlap=$o"; timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e --overlap $o 2>&1 | python -c "
 import sys, json

@@ -1,7 +1,7 @@
 #!/bin/bash
 # parity tests on the default build, then a device-resident bench for each tuning build named on the command line
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
 for lib in "$@"; do
   echo "== $lib"
   RV_B200_LIB=$lib timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu --no-e2e 2>&1 | python -c "
