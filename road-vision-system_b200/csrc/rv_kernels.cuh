@@ -898,6 +898,21 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
         const bool al4 = ((reinterpret_cast<uintptr_t>(dframe) & 3) == 0) && (a.dpitch % 4 == 0);
         const int rows = min(TILE_H, g.H - y0);
         constexpr int WPR = O_STRIDE / 4;                        // 90 words per row
+        const bool al8 = ((reinterpret_cast<uintptr_t>(dframe) & 7) == 0) && (a.dpitch % 8 == 0);
+        if (al8 && nb == 3 * TILE_W && rows == TILE_H) {
+            // full tile, 8-byte aligned rows (3*x0 = 360*bx): 45 double words per row, four rows per warp, fully unrolled
+            uint8_t *dp = dframe + (size_t)(y0 + warp) * a.dpitch + 3 * (size_t)x0 + 8 * lane;
+            const uint8_t *op = O + warp * O_STRIDE + 8 * lane;
+            const size_t dstep = (size_t)CHAIN_WARPS * a.dpitch;
+#pragma unroll
+            for (int k = 0; k < TILE_H / CHAIN_WARPS; ++k) {
+                const uint2 v0 = *reinterpret_cast<const uint2 *>(op);
+                *reinterpret_cast<uint2 *>(dp) = v0;
+                if (lane < 45 - 32) *reinterpret_cast<uint2 *>(dp + 256) = *reinterpret_cast<const uint2 *>(op + 256);
+                dp += dstep;
+                op += CHAIN_WARPS * O_STRIDE;
+            }
+        } else
         for (int ry = warp; ry < rows; ry += CHAIN_WARPS) {
             uint8_t *dp = dframe + (size_t)(y0 + ry) * a.dpitch + 3 * (size_t)x0;
             const uint32_t *orow = reinterpret_cast<const uint32_t *>(O + ry * O_STRIDE);

@@ -18,6 +18,10 @@ from .ops import median_derain as _median
 from .registry import get_op_class
 
 
+def _is_cuda_tensor(x):
+    return type(x).__module__.startswith("torch") and hasattr(x, "is_cuda") and x.is_cuda
+
+
 class PreprocessPipeline:
     def __init__(self, config: Dict[str, Any]):
         self.enabled = bool(config.get("enabled", True))
@@ -89,8 +93,10 @@ class PreprocessPipeline:
         and D2H of consecutive chunks overlap).  Frames the low-contrast gate skips are copied
         through unchanged.
         """
+        if _is_cuda_tensor(frames):
+            return self._process_batch_device(frames, out)
         if not isinstance(frames, np.ndarray) or frames.ndim != 4 or frames.shape[3] != 3 or frames.dtype != np.uint8:
-            raise ValueError("frames must be a (B,H,W,3) uint8 numpy array")
+            raise ValueError("frames must be a (B,H,W,3) uint8 numpy array (or a torch CUDA uint8 tensor of that shape)")
         if not self.enabled or not self.ops:
             if out is None:
                 return frames
@@ -124,6 +130,33 @@ class PreprocessPipeline:
                 if last and out is not None:
                     np.copyto(out, cur)
                     cur = out
+        return cur
+
+    def _process_batch_device(self, frames, out=None):
+        """Device-resident batch: a contiguous torch CUDA uint8 tensor (B,H,W,3) in, a tensor of the same kind out.
+        Work is enqueued on torch's current stream (no host synchronisation): use the result with torch as usual."""
+        import torch
+        if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3 or not frames.is_contiguous():
+            raise ValueError("frames must be a contiguous (B,H,W,3) uint8 CUDA tensor")
+        if not self.enabled or not self.ops:
+            return frames if out is None else out.copy_(frames)
+        if self._gate()[0]:
+            raise ValueError("the low-contrast gate is not supported for device-resident batches; use numpy frames")
+        ctx = default_context(frames.device.index)
+        b, h, w, _ = frames.shape
+        segs = self._segments()
+        if not all(isinstance(sg, Params) for sg in segs):
+            raise ValueError("device-resident batches support only CLAHEDehaze / MedianDerain chains")
+        stream = torch.cuda.current_stream(frames.device).cuda_stream
+        cur = frames
+        for idx, sg in enumerate(segs):
+            dst = out if (idx == len(segs) - 1 and out is not None) else torch.empty_like(frames)
+            if stream == 0:        # legacy default stream: run on the context's stream, synchronously
+                torch.cuda.current_stream(frames.device).synchronize()
+                ctx.chain_device(cur.data_ptr(), dst.data_ptr(), b, h, w, sg)
+            else:
+                ctx.submit_device(cur.data_ptr(), dst.data_ptr(), b, h, w, sg, stream=stream)
+            cur = dst
         return cur
 
     # -- new: chain fused with the detector-input stage (SURVEY.md 8f-1) ------------------------

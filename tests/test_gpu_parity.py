@@ -282,3 +282,24 @@ def test_letterbox_stage_and_fused_chain(ctx):
                 assert np.array_equal(t[i].view(np.uint16), O.letterbox_f16(proc, size).view(np.uint16)), (h, w, k, want_full, i)
                 if want_full:
                     assert np.array_equal(full[i], proc)
+
+
+def test_process_batch_torch_cuda_tensor(ctx):
+    """Device-resident entry: torch CUDA tensor in, torch CUDA tensor out, on torch's current stream."""
+    torch = pytest.importorskip("torch")
+    import rvb200
+    from rvb200 import synth
+    frames = synth.frame_pool(270, 480, 4, base_seed=120)
+    cfg = {"chain": [{"name": "CLAHEDehaze", "params": {"space": "LAB"}}, {"name": "MedianDerain", "params": {"ksize": 5}}]}
+    pl = rvb200.PreprocessPipeline(cfg)
+    want = pl.process_batch(frames)
+    d = torch.from_numpy(frames).cuda()
+    got = pl.process_batch(d)                                   # default stream -> synchronous path
+    assert got.is_cuda and got.data_ptr() != d.data_ptr()
+    assert np.array_equal(got.cpu().numpy(), want)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        out = torch.empty_like(d)
+        res = pl.process_batch(d, out=out)                      # asynchronous on stream s
+    s.synchronize()
+    assert res is out and np.array_equal(out.cpu().numpy(), want)
