@@ -255,6 +255,46 @@ def build5_quads(M, parity):
     return d, inputs, outs
 
 
+def build_hier(k, M, parity):
+    """Any odd k: sorted columns -> pairs P(a) (a of the given parity) -> H(a) = the (k-1)/2 pairs a, a+2, ... merged left
+    to right, after every merge keeping only the ranks that can still hold the median of k*k -> median = one rank of
+    H(a) u the remaining column.  H(a) serves outputs a-1 and a; for k = 5 this is the quads scheme."""
+    d = Dag()
+    ncol = M + k - 1
+    inputs = [[d.inp((c, r)) for r in range(k)] for c in range(ncol)]
+    cols = [d.sort(col) for col in inputs]
+    half = (k * k) // 2
+    P, H = {}, {}
+
+    def pair(a):
+        if a not in P:
+            P[a] = d.merge(cols[a], cols[a + 1])
+        return P[a]
+
+    def trim(lst, below, rest):
+        t = half - below
+        lo, hi = max(0, t - rest), min(len(lst) - 1, t)
+        return lst[lo:hi + 1], below + lo
+
+    def hexa(a):
+        if a not in H:
+            npairs = (k - 1) // 2
+            acc, below, used = pair(a), 0, 2
+            for i in range(1, npairs):
+                used += 2
+                acc, below = trim(d.merge(acc, pair(a + 2 * i)), below, (k - used) * k)
+            if npairs == 1:
+                acc, below = trim(acc, 0, k)
+            H[a] = (acc, below)
+        return H[a]
+
+    outs = []
+    for o in range(M):
+        (acc, below), single = (hexa(o), cols[o + k - 1]) if o % 2 == parity else (hexa(o + 1), cols[o])
+        outs.append(d.kth2(acc, single, half - below + 1))
+    return d, inputs, outs
+
+
 def build5_2rows(M, parity, rparity=0):
     """5x5, two vertically adjacent output rows per call (window rows 0..4 and 1..5 of six input rows): the four
     middle rows are shared.  Columns of the middle rows are sorted once (sort4), merged in pairs P4 and quads Q4
@@ -478,7 +518,7 @@ def emit(d, inputs, outs, k, M, fh):
     return nops
 
 
-CONFIG = {3: 4, 5: int(os.environ.get('RV_MEDIAN5_M', '6')), 7: 2, 9: 2}     # k -> outputs per call
+CONFIG = {3: 4, 5: int(os.environ.get('RV_MEDIAN5_M', '6')), 7: int(os.environ.get('RV_MEDIAN7_M', '4')), 9: 2}     # k -> outputs per call
 
 
 def main():
@@ -497,8 +537,10 @@ def main():
                  "#ifndef RV_CEX\n#define RV_CEX(n, lo, hi, a, b) const uint32_t lo = RV_MN(a, b), hi = RV_MX(a, b)\n#endif\n\n")
         for k, M in CONFIG.items():
             best = None
-            for strat, parity in (("pairs", 0), ("pairs", 1), ("flat", 0), ("quads", 0), ("quads", 1)):
-                if strat == "quads":
+            for strat, parity in (("pairs", 0), ("pairs", 1), ("flat", 0), ("quads", 0), ("quads", 1), ("hier", 0), ("hier", 1)):
+                if strat == "hier":
+                    d, inputs, outs = build_hier(k, M, parity)
+                elif strat == "quads":
                     if k != 5:
                         continue
                     d, inputs, outs = build5_quads(M, parity)
