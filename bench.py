@@ -157,6 +157,28 @@ def cpu_chain_fps(frames, budget_s, mode):
     return n / dt, cores, n
 
 
+def bind_near_gpu(index):
+    """Pin this rank to the host cores next to its GPU (PCI device's local_cpulist) so that pinned staging buffers are
+    first-touched on the GPU's NUMA node; with 8 ranks the end-to-end leg is host-memory bound.  Best effort."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        txt = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return f"{len(use)} cores local to {bdf}"
+        return "affinity unchanged (all allowed cores are local or none is)"
+    except Exception as e:        # noqa: BLE001
+        return f"affinity unchanged ({type(e).__name__})"
+
+
 def make_pool():
     import rvb200  # noqa: F401  (package import only; no GPU needed for the generator)
     from rvb200 import synth
@@ -215,6 +237,7 @@ def run_gpu(args, rank, world, local_rank):
     import rvb200
 
     torch.cuda.set_device(local_rank)
+    numa = bind_near_gpu(local_rank) if world > 1 else "single rank: not bound"
     ctx = rvb200.Context(local_rank)
     if args.group:
         ctx.set_option("group_frames", args.group)
@@ -319,6 +342,7 @@ def run_gpu(args, rank, world, local_rank):
     line = base_line(world, args.steps, args.warmup)
     line.update({
         "value": value, "ms_per_step": ms_max / args.steps, "gpu_launches": launches, "clocks": clocks,
+        "host_affinity": numa,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * FRAME_BYTES, "d2h_bytes_per_step": BATCH * FRAME_BYTES,
                 "steps": e2e_steps, "api": "PreprocessPipeline.process_batch(pinned in, pinned out)"},
         "roofline": {"bound": "hbm", "kernel": "k_chain<YCrCb,5>", "achieved": achieved, "peak": peak, "unit": "GB/s",
