@@ -10,7 +10,7 @@
  *                 groups in flight per thread), optional gray min/max (low-contrast gate) and luma plane (tests)
  *   k_build_lut   clip + redistribute + prefix sum -> u8 LUT per tile (one warp per tile, shuffle scans) and the
  *                 four-LUT "quad" tables used by the interpolation
- *   k_chain       per 120x32 output tile: TMA box load (cp.async.bulk.tensor + mbarrier), forward colour conversion,
+ *   k_chain       per 120x48 output tile: TMA box load (cp.async.bulk.tensor + mbarrier), forward colour conversion,
  *                 bilinear four-LUT blend in float32 without FMA contraction, inverse colour conversion, packed
  *                 saturation into u16x2 planes, k x k median (generated selection networks, half the compare-
  *                 exchanges on the FMA pipe, two output rows per task for 5x5), coalesced store; optionally the
@@ -444,7 +444,10 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 constexpr int TILE_W = 120;            // output pixels per tile row
 constexpr int BOX_W = 128;             // staged pixels per row: 4 left + 120 + 4 right
 constexpr int LPAD = 4;
-constexpr int TILE_H = 32;
+#ifndef RV_TILE_H
+#define RV_TILE_H 48
+#endif
+constexpr int TILE_H = RV_TILE_H;
 constexpr int HALF = TILE_H / 2;       // u16x2 lanes of the median hold rows (s, s + HALF)
 constexpr int CHAIN_THREADS = 256;
 constexpr int CHAIN_WARPS = CHAIN_THREADS / 32;
