@@ -449,7 +449,10 @@ constexpr int LPAD = 4;
 #endif
 constexpr int TILE_H = RV_TILE_H;
 constexpr int HALF = TILE_H / 2;       // u16x2 lanes of the median hold rows (s, s + HALF)
-constexpr int CHAIN_THREADS = 256;
+#ifndef RV_CHAIN_THREADS
+#define RV_CHAIN_THREADS 256
+#endif
+constexpr int CHAIN_THREADS = RV_CHAIN_THREADS;
 constexpr int CHAIN_WARPS = CHAIN_THREADS / 32;
 constexpr int A_STRIDE = BOX_W * 3 + 16; // bytes per staged BGR row: the box starts at the 16-byte boundary at or below
                                        // pixel x0-LPAD (a TMA box must start 16-byte aligned), so up to 12 bytes of slack
