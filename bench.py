@@ -367,9 +367,9 @@ def run_gpu(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
-# DRAM bytes of one k_chain launch (64 x 1080p frames: dram__bytes_read.sum 403.5 MB + dram__bytes_write.sum 356.9 MB) from the
-# committed `ncu --set full` capture profiles/r1_v4_k_chain_summary.txt; algorithmic bytes of that launch: 796.3 MB
-TRAFFIC_NCU = 760.4e6
+# DRAM bytes of one k_chain launch (64 x 1080p frames: dram__bytes_read.sum 403.5 MB + dram__bytes_write.sum 355.0 MB) from the
+# committed `ncu --set full` capture profiles/r1_v6_k_chain_summary.txt; algorithmic bytes of that launch: 796.3 MB
+TRAFFIC_NCU = 758.6e6
 
 
 def main():
