@@ -134,6 +134,7 @@ class Context:
         self._h = h
         self.device = int(device)
         self._pinned = {}          # base address -> nbytes
+        self._pin_pool = {}        # nbytes -> [free page-locked blocks] (results of per-frame calls)
         self._finalizer = weakref.finalize(self, self._lib.rv_destroy, h)
 
     # -- plumbing ------------------------------------------------------------------------
@@ -171,6 +172,33 @@ class Context:
         weakref.finalize(buf, _free)
         return arr
 
+    def _pooled_pinned(self, shape, dtype=np.uint8, keep=4):
+        """Like pinned_empty, but the page-locked block goes back to a small per-size pool when the array dies, so a
+        per-frame loop (`proc = pipeline(raw)`, main_preview.py:94) gets DMA-able result arrays without paying
+        cudaHostAlloc per call.  The array is the caller's: fresh, writable, never aliased while it is alive."""
+        nbytes = max(int(np.prod(shape)) * np.dtype(dtype).itemsize, 1)
+        free = self._pin_pool.setdefault(nbytes, [])
+        if free:
+            addr = free.pop()
+        else:
+            p = C.c_void_p()
+            self._ck(self._lib.rv_alloc_pinned(self._h, nbytes, C.byref(p)))
+            addr = p.value
+            self._pinned[addr] = nbytes
+        buf = (C.c_uint8 * nbytes).from_address(addr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        owner = self
+
+        def _recycle(addr=addr, nbytes=nbytes):
+            pool = owner._pin_pool.setdefault(nbytes, [])
+            if len(pool) < keep:
+                pool.append(addr)
+            else:
+                owner._pinned.pop(addr, None)
+                owner._lib.rv_free_pinned(owner._h, C.c_void_p(addr))
+        weakref.finalize(buf, _recycle)
+        return arr
+
     def mem_kind(self, arr):
         a = arr.ctypes.data
         for base, n in self._pinned.items():
@@ -186,7 +214,8 @@ class Context:
             frames = np.ascontiguousarray(frames)
         n, h, w, _ = frames.shape
         if out is None:
-            out = np.empty_like(frames)
+            # small results (the per-frame contract) land in recycled page-locked memory: the D2H copy is a plain DMA
+            out = self._pooled_pinned(frames.shape) if frames.nbytes <= (64 << 20) else np.empty_like(frames)
         elif out.shape != frames.shape or out.dtype != np.uint8 or not out.flags.c_contiguous:
             raise ValueError("out must be a C-contiguous uint8 array of the input's shape")
         kind = MEM_PINNED if (self.mem_kind(frames) == MEM_PINNED and self.mem_kind(out) == MEM_PINNED) else MEM_HOST
@@ -255,7 +284,7 @@ class Context:
         _check_frames(frames)
         frames = np.ascontiguousarray(frames)
         n, h, w, _ = frames.shape
-        out = np.empty_like(frames)
+        out = self._pooled_pinned(frames.shape) if frames.nbytes <= (64 << 20) else np.empty_like(frames)
         self._ck(self._lib.rv_clahe_dehaze(self._h, frames.ctypes.data, out.ctypes.data, n, h, w, 3 * w, 3 * w,
                                            SPACE_LAB if space == "LAB" else SPACE_YCRCB, float(clip_limit), int(grid), MEM_HOST))
         return out
@@ -264,7 +293,7 @@ class Context:
         _check_frames(frames)
         frames = np.ascontiguousarray(frames)
         n, h, w, _ = frames.shape
-        out = np.empty_like(frames)
+        out = self._pooled_pinned(frames.shape) if frames.nbytes <= (64 << 20) else np.empty_like(frames)
         self._ck(self._lib.rv_median(self._h, frames.ctypes.data, out.ctypes.data, n, h, w, 3 * w, 3 * w, int(ksize), MEM_HOST))
         return out
 
