@@ -24,7 +24,7 @@
  * There is NO CPU fallback: without a usable sm_100 device rv_create fails.
  *
  * Frames are uint8 BGR, interleaved, `h` rows of `w` pixels, `pitch` bytes between rows
- * (pitch >= 3*w), `n` frames `frame_stride` bytes apart (0 means h*pitch).
+ * (pitch >= 3*w), `n` frames h*pitch bytes apart.  `in` and `out` must not alias (in-place is rejected).
  */
 #ifndef RV_B200_H
 #define RV_B200_H

@@ -793,6 +793,7 @@ int rv_submit(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w,
     RV_TRY(check_frames(ctx, in, out, n, h, w, in_pitch, out_pitch));
     RV_TRY(check_params(ctx, p));
     if (!p->clahe && p->ksize == 0) return fail(ctx, RV_ERR_ARG, "nothing to do (no CLAHE, no median)");
+    if (in == out) return fail(ctx, RV_ERR_ARG, "in-place operation is not supported (tiles read their neighbours' halo)");
     if (n == 0) return RV_OK;
     CK(cudaSetDevice(ctx->device));
     if (mem_kind == RV_MEM_DEVICE)
@@ -808,6 +809,7 @@ int rv_chain_u8(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int 
     RV_TRY(check_frames(ctx, in, out, n, h, w, in_pitch, out_pitch));
     RV_TRY(check_params(ctx, p));
     if (!p->clahe && p->ksize == 0) return fail(ctx, RV_ERR_ARG, "nothing to do (no CLAHE, no median)");
+    if (in == out) return fail(ctx, RV_ERR_ARG, "in-place operation is not supported (tiles read their neighbours' halo)");
     if (n == 0) return RV_OK;
     CK(cudaSetDevice(ctx->device));
     if (mem_kind == RV_MEM_DEVICE) {

@@ -303,3 +303,22 @@ def test_process_batch_torch_cuda_tensor(ctx):
         res = pl.process_batch(d, out=out)                      # asynchronous on stream s
     s.synchronize()
     assert res is out and np.array_equal(out.cpu().numpy(), want)
+
+
+def test_argument_errors(ctx):
+    """Bad arguments fail loudly with ValueError (RV_ERR_ARG), nothing is computed."""
+    torch = pytest.importorskip("torch")
+    import rvb200
+    img = np.zeros((1, 16, 16, 3), np.uint8)
+    for bad in (dict(ksize=4), dict(ksize=11), dict(grid=1), dict(grid=1000)):
+        kw = dict(space="YCrCb", clip_limit=2.0, grid=8, ksize=3)
+        kw.update(bad)
+        with pytest.raises(ValueError):
+            ctx.chain(img, rvb200.Params.make(**kw))
+    with pytest.raises(ValueError):
+        ctx.chain(img, rvb200.Params.make(ksize=0, clahe=False))            # nothing to do
+    d = torch.zeros(16 * 16 * 3, dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError):
+        ctx.chain_device(d.data_ptr(), d.data_ptr(), 1, 16, 16, rvb200.Params.make())   # in-place
+    with pytest.raises(ValueError):
+        ctx.chain(np.zeros((1, 16, 16, 3), np.float32), rvb200.Params.make())
