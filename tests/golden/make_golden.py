@@ -98,5 +98,25 @@ def main():
     print("wrote", len(cases), "cases,", len(pins), "pins;", os.path.getsize(os.path.join(HERE, "chain_small.npz")), "bytes")
 
 
+
+
+def full_size_fog_fixture():
+    """One 1280x720 frame fogged by the reference's synthesiser (fog_batch.py parameters, seed 7) + rain, stored as PNG
+    bytes, with SHA-1 of the reference PreprocessPipeline output for the default.yaml chain and the LAB/k5 chain."""
+    clean = synth.clean_scene(720, 1280, 777)
+    fog = EnhancedFogSynthesizer(level="medium", y_h_ratio=0.42, perlin_scale_ratio=0.18, perlin_octaves=2,
+                                 horizon_softness=0.07, global_veil=0.5, depth_blur_max=4.0, seed=7)
+    frame = synth.add_rain(fog.synthesize(clean)[0], seed=7)
+    ok, png = cv2.imencode(".png", frame, [cv2.IMWRITE_PNG_COMPRESSION, 9])
+    assert ok and np.array_equal(cv2.imdecode(png, cv2.IMREAD_COLOR), frame)
+    shas = []
+    for space, grid, k in (("YCrCb", 8, 3), ("LAB", 8, 5)):
+        ref = PreprocessPipeline(ref_cfg(space, 2.0, grid, k))(frame)
+        shas.append(f"{space}|{grid}|{k}|{hashlib.sha1(ref.tobytes()).hexdigest()}")
+    np.savez(os.path.join(HERE, "fog_720p.npz"), png=png, shas=np.array(shas))
+    print("fog_720p.npz:", os.path.getsize(os.path.join(HERE, "fog_720p.npz")), "bytes")
+
+
 if __name__ == "__main__":
     main()
+    full_size_fog_fixture()

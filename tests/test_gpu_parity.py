@@ -322,3 +322,17 @@ def test_argument_errors(ctx):
         ctx.chain_device(d.data_ptr(), d.data_ptr(), 1, 16, 16, rvb200.Params.make())   # in-place
     with pytest.raises(ValueError):
         ctx.chain(np.zeros((1, 16, 16, 3), np.float32), rvb200.Params.make())
+
+
+def test_full_size_reference_fog_fixture_gpu(ctx):
+    """The reference-fogged 720p frame (tests/golden/fog_720p.npz): CUDA output hashes equal the reference pipeline's."""
+    cv2 = pytest.importorskip("cv2")
+    import os
+    import rvb200
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "fog_720p.npz"))
+    frame = cv2.imdecode(z["png"], cv2.IMREAD_COLOR)
+    for line in z["shas"]:
+        space, grid, k, sha = str(line).split("|")
+        got = ctx.chain(frame[None], rvb200.Params.make(space, 2.0, int(grid), int(k)))[0]
+        assert hashlib.sha1(got.tobytes()).hexdigest() == sha, (space, grid, k)

@@ -172,3 +172,20 @@ def test_lab_forward_ranges():
     a = (500 * (fX - fY) + (128 << 15) + 16384) >> 15
     b = (200 * (fY - fZ) + (128 << 15) + 16384) >> 15
     assert (a.min(), a.max(), b.min(), b.max()) == (42, 226, 20, 223)
+
+
+def _fog_720p():
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "fog_720p.npz"))
+    frame = cv2.imdecode(z["png"], cv2.IMREAD_COLOR)
+    return frame, [str(s).split("|") for s in z["shas"]]
+
+
+def test_full_size_reference_fog_fixture():
+    """A 1280x720 frame fogged by the reference's own EnhancedFogSynthesizer; SHA-1 of the reference pipeline's outputs."""
+    frame, shas = _fog_720p()
+    assert frame.shape == (720, 1280, 3)
+    for space, grid, k, sha in shas:
+        got = O.chain(frame, O.SPACE_LAB if space == "LAB" else O.SPACE_YCRCB, 2.0, int(grid), int(k))
+        assert hashlib.sha1(got.tobytes()).hexdigest() == sha, (space, grid, k)
