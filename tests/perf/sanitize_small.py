@@ -1,12 +1,12 @@
 #!/usr/bin/env python3
 """Smallest end-to-end exercise of every kernel for compute-sanitizer (one tool per gpurun call):
-    compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+    compute-sanitizer --tool memcheck python tests/perf/sanitize_small.py"""
 import os
 import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import rvb200
 from oracle import rv_oracle as O
 

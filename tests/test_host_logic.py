@@ -39,6 +39,16 @@ def test_no_cpu_fallback_without_gpu():
         op(np.zeros((8, 8, 3), np.uint8))
 
 
+def test_only_tests_smoke_and_bench_use_the_oracle():
+    """oracle/ is test infrastructure: nothing under tools/ or the product package may import it."""
+    for sub in ("tools", "road-vision-system_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith((".py", ".sh", ".cu", ".cuh", ".h")):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert "from oracle" not in text and "import oracle" not in text and "rv_oracle" not in text, (sub, f)
+
+
 def test_product_never_touches_the_oracle():
     pkg = os.path.join(ROOT, "road-vision-system_b200")
     for dirpath, _, files in os.walk(pkg):
