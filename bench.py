@@ -117,6 +117,7 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- CPU arm (reference's cv2 calls)
 def _cpu_worker(args):
+    """Runs in a *spawned* worker (never forked: a forked child inherits cv2's thread-pool state and can deadlock)."""
     import cv2
     from oracle import cv2_chain
     cv2.setNumThreads(1)
@@ -148,7 +149,7 @@ def cpu_chain_fps(frames, budget_s, mode):
     per = 2
     reps = max(1, int(budget_s / (0.04 * per)))          # ~40 ms per 1080p frame on one core
     reps = min(reps, 8)
-    with mp.get_context("fork").Pool(cores) as pool:
+    with mp.get_context("spawn").Pool(cores) as pool:
         pool.map(_cpu_worker, [([frames[0]], 1)] * cores)         # warm the workers
         t0 = time.perf_counter()
         pool.map(_cpu_worker, [([frames[i % len(frames)] for i in range(c, c + per)], reps) for c in range(cores)])
@@ -205,7 +206,7 @@ def run_reference(args, rank, world):
     cores = len(os.sched_getaffinity(0))
     sample = min(max(16, 2 * cores), 4 * BATCH)   # frames per step: two per worker so every host core stays busy
     frames = [pool[i % POOL] for i in range(sample)]
-    with mp.get_context("fork").Pool(cores) as pp:
+    with mp.get_context("spawn").Pool(cores) as pp:
         chunks = [[f for f in frames[c::cores]] for c in range(cores)]
         chunks = [c for c in chunks if c]
         for _ in range(max(args.warmup, 1)):
@@ -351,11 +352,11 @@ def run_gpu(args, rank, world, local_rank):
                      "traffic": TRAFFIC_NCU},
     })
     if world == 1 and not args.no_cpu:
+        fps_p, cores_p, n_p = cpu_chain_fps(list(pool), 6.0, "procs")
         from oracle import cv2_chain            # the CPU leg doubles as the checker: never report a wrong kernel's speed
         if not np.array_equal(gpu_first, cv2_chain.chain(host[0], SPACE, CLIP, GRID, KSIZE)):
             raise SystemExit("bench: CUDA chain differs from the reference's cv2 chain; refusing to report")
         line["parity"] = "frame 0 of the timed batch bit-exact vs the reference's cv2 chain"
-        fps_p, cores_p, n_p = cpu_chain_fps(list(pool), 6.0, "procs")
         fps_t, cores_t, n_t = cpu_chain_fps(list(pool[:4]), 4.0, "threads")
         import cv2
         best = max(fps_p, fps_t)
