@@ -116,16 +116,25 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU arm (reference's cv2 calls)
+_WORKER_FRAMES = None
+
+
+def _cpu_init(frames):
+    """Pool initializer: every spawned worker receives the frame pool once, outside any timed region."""
+    global _WORKER_FRAMES
+    import cv2
+    cv2.setNumThreads(1)
+    _WORKER_FRAMES = frames
+
+
 def _cpu_worker(args):
     """Runs in a *spawned* worker (never forked: a forked child inherits cv2's thread-pool state and can deadlock)."""
-    import cv2
     from oracle import cv2_chain
-    cv2.setNumThreads(1)
-    frames, reps = args
+    idx, reps = args
     t0 = time.perf_counter()
     for _ in range(reps):
-        for f in frames:
-            cv2_chain.chain(f, SPACE, CLIP, GRID, KSIZE)
+        for i in idx:
+            cv2_chain.chain(_WORKER_FRAMES[i % len(_WORKER_FRAMES)], SPACE, CLIP, GRID, KSIZE)
     return time.perf_counter() - t0
 
 
@@ -149,10 +158,10 @@ def cpu_chain_fps(frames, budget_s, mode):
     per = 2
     reps = max(1, int(budget_s / (0.04 * per)))          # ~40 ms per 1080p frame on one core
     reps = min(reps, 8)
-    with mp.get_context("spawn").Pool(cores) as pool:
-        pool.map(_cpu_worker, [([frames[0]], 1)] * cores)         # warm the workers
+    with mp.get_context("spawn").Pool(cores, initializer=_cpu_init, initargs=(list(frames),)) as pool:
+        pool.map(_cpu_worker, [([0], 1)] * cores)                 # warm the workers
         t0 = time.perf_counter()
-        pool.map(_cpu_worker, [([frames[i % len(frames)] for i in range(c, c + per)], reps) for c in range(cores)])
+        pool.map(_cpu_worker, [(list(range(c, c + per)), reps) for c in range(cores)])
         dt = time.perf_counter() - t0
     n = cores * per * reps
     return n / dt, cores, n
@@ -206,8 +215,8 @@ def run_reference(args, rank, world):
     cores = len(os.sched_getaffinity(0))
     sample = min(max(16, 2 * cores), 4 * BATCH)   # frames per step: two per worker so every host core stays busy
     frames = [pool[i % POOL] for i in range(sample)]
-    with mp.get_context("spawn").Pool(cores) as pp:
-        chunks = [[f for f in frames[c::cores]] for c in range(cores)]
+    with mp.get_context("spawn").Pool(cores, initializer=_cpu_init, initargs=(list(pool),)) as pp:
+        chunks = [list(range(c, sample, cores)) for c in range(cores)]
         chunks = [c for c in chunks if c]
         for _ in range(max(args.warmup, 1)):
             pp.map(_cpu_worker, [(c, 1) for c in chunks])
