@@ -10,7 +10,10 @@ from oracle import rv_oracle as O
 cv2 = pytest.importorskip("cv2")
 from oracle import cv2_chain as R  # noqa: E402
 
-shapes = st.tuples(st.integers(1, 96), st.integers(1, 140))
+import os
+
+BIG = int(os.environ.get("RV_PROP_SCALE", "1"))          # RV_PROP_SCALE=4: one-off deeper stress (bigger frames, 4x the examples)
+shapes = st.tuples(st.integers(1, 96 * BIG), st.integers(1, 140 * BIG))
 grids = st.sampled_from([2, 3, 5, 7, 8, 13, 16, 32])
 clips = st.sampled_from([0.0, -1.0, 0.001, 0.5, 2.0, 3.7, 40.0, 1000.0])
 ksizes = st.sampled_from([0, 3, 5, 7, 9])
@@ -42,7 +45,7 @@ def test_oracle_equals_cv2(shape, grid, clip, k, space, kind, seed):
 
 
 @pytest.mark.gpu
-@settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=120 * BIG, deadline=None, suppress_health_check=list(HealthCheck))
 @given(shapes, grids, clips, ksizes, spaces, kinds, st.integers(0, 10_000), st.integers(1, 3))
 def test_gpu_equals_oracle(shape, grid, clip, k, space, kind, seed, n):
     import rvb200
@@ -55,7 +58,7 @@ def test_gpu_equals_oracle(shape, grid, clip, k, space, kind, seed, n):
 
 
 @pytest.mark.gpu
-@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=40 * BIG, deadline=None, suppress_health_check=list(HealthCheck))
 @given(st.tuples(st.integers(1, 200), st.integers(1, 300)), st.sampled_from([32, 64, 96, 160]), kinds, st.integers(0, 10_000))
 def test_gpu_letterbox_equals_oracle(shape, size, kind, seed):
     import rvb200
