@@ -336,3 +336,22 @@ def test_full_size_reference_fog_fixture_gpu(ctx):
         space, grid, k, sha = str(line).split("|")
         got = ctx.chain(frame[None], rvb200.Params.make(space, 2.0, int(grid), int(k)))[0]
         assert hashlib.sha1(got.tobytes()).hexdigest() == sha, (space, grid, k)
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """A C program (gcc, no Python / torch types) drives the library through include/rv_b200.h and checks it against the C oracle."""
+    import os
+    import shutil
+    import subprocess
+    import rvb200
+    from oracle import rv_oracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    so, oso = rvb200.library_path(), rv_oracle.build()
+    exe = str(tmp_path / "c_abi_smoke")
+    subprocess.check_call(["gcc", "-O1", "-o", exe, os.path.join(root, "tests", "c_abi_smoke.c"), "-I", os.path.join(root, "include"),
+                           so, oso, "-lm", "-Wl,-rpath," + os.path.dirname(so), "-Wl,-rpath," + os.path.dirname(oso)])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "mismatches 0" in r.stdout
