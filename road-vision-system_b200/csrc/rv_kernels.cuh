@@ -56,10 +56,17 @@ __device__ __forceinline__ void rv_ce_fma(uint32_t a, uint32_t b, uint32_t &lo, 
     hi = *reinterpret_cast<const uint32_t *>(&h);
     lo = *reinterpret_cast<const uint32_t *>(&l);
 }
-#define RV_CEX(n, lo, hi, a, b)                                            \
-    uint32_t lo, hi;                                                       \
-    if constexpr (((n) % RV_FMA_DEN) < RV_FMA_NUM) rv_ce_fma(a, b, lo, hi); \
+#define RV_CEX_MIX(num, den, n, lo, hi, a, b)                      \
+    uint32_t lo, hi;                                               \
+    if constexpr (((n) % (den)) < (num)) rv_ce_fma(a, b, lo, hi);  \
     else { lo = __vminu2(a, b); hi = __vmaxu2(a, b); }
+#define RV_CEX(n, lo, hi, a, b) RV_CEX_MIX(RV_FMA_NUM, RV_FMA_DEN, n, lo, hi, a, b)
+// the 3x3 network has few full compare-exchanges (26 of 80 ops); its kernel is ALU-heavier, so more of them go to the FMA pipe
+#ifndef RV_FMA3_NUM
+#define RV_FMA3_NUM 1
+#define RV_FMA3_DEN 2
+#endif
+#define RV_CEX3(n, lo, hi, a, b) RV_CEX_MIX(RV_FMA3_NUM, RV_FMA3_DEN, n, lo, hi, a, b)
 
 #include "rv_median_net.h"
 

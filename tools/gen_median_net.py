@@ -386,7 +386,7 @@ def emit_2rows(d, inp, outs, M, fh):
         if n in partner:
             lo, hi = (n, partner[n]) if op == "min" else (partner[n], n)
             name[lo], name[hi] = f"t{lo}", f"t{hi}"
-            fh.write(f"    RV_CEX({ce}, t{lo}, t{hi}, {name[a]}, {name[b]});\n")
+            fh.write(f"    RV_CEX5X2({ce}, t{lo}, t{hi}, {name[a]}, {name[b]});\n")
             done.update((lo, hi))
             ce += 1
         else:
@@ -505,7 +505,7 @@ def emit(d, inputs, outs, k, M, fh):
         if n in partner:
             lo, hi = (n, partner[n]) if op == "min" else (partner[n], n)
             name[lo], name[hi] = f"t{lo}", f"t{hi}"
-            fh.write(f"    RV_CEX({ce}, t{lo}, t{hi}, {name[a]}, {name[b]});\n")
+            fh.write(f"    RV_CEX{k}({ce}, t{lo}, t{hi}, {name[a]}, {name[b]});\n")
             done.update((lo, hi))
             ce += 1
         else:
@@ -534,7 +534,11 @@ def main():
                  " * out[o]: median of columns o..o+k-1.  Verified by the generator (0-1 principle for k<=5, random for all). */\n"
                  "#ifndef RV_MEDIAN_NET_H\n#define RV_MEDIAN_NET_H\n#include <stdint.h>\n"
                  "#ifndef RV_MN\n#define RV_MN(a, b) __vminu2((a), (b))\n#define RV_MX(a, b) __vmaxu2((a), (b))\n#endif\n"
-                 "#ifndef RV_CEX\n#define RV_CEX(n, lo, hi, a, b) const uint32_t lo = RV_MN(a, b), hi = RV_MX(a, b)\n#endif\n\n")
+                 "#ifndef RV_CEX\n#define RV_CEX(n, lo, hi, a, b) const uint32_t lo = RV_MN(a, b), hi = RV_MX(a, b)\n#endif\n"
+                 "/* per-network compare-exchange macros (the kernel may give each network its own ALU/FMA mix) */\n"
+                 "#ifndef RV_CEX3\n#define RV_CEX3 RV_CEX\n#endif\n#ifndef RV_CEX5\n#define RV_CEX5 RV_CEX\n#endif\n"
+                 "#ifndef RV_CEX7\n#define RV_CEX7 RV_CEX\n#endif\n#ifndef RV_CEX9\n#define RV_CEX9 RV_CEX\n#endif\n"
+                 "#ifndef RV_CEX5X2\n#define RV_CEX5X2 RV_CEX\n#endif\n\n")
         for k, M in CONFIG.items():
             best = None
             for strat, parity in (("pairs", 0), ("pairs", 1), ("flat", 0), ("quads", 0), ("quads", 1), ("hier", 0), ("hier", 1)):
