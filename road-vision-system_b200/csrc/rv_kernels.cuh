@@ -46,6 +46,9 @@
 #ifndef RV_MEDIAN5_2ROW
 #define RV_MEDIAN5_2ROW 1
 #endif
+#ifndef RV_MEDIAN3_2ROW
+#define RV_MEDIAN3_2ROW 1
+#endif
 __device__ __forceinline__ void rv_ce_fma(uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi)
 {
     const __half2 x = *reinterpret_cast<const __half2 *>(&a), y = *reinterpret_cast<const __half2 *>(&b);
@@ -844,13 +847,15 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
     __syncthreads();
 
     // ---- phase 2: k x k median per channel plane; lanes of each u16x2 are output rows (s, s+HALF)
-#if RV_MEDIAN5_2ROW
-    if constexpr (K == 5) {
-        // two vertically adjacent output rows per task (slots s, s+1): the four middle window rows are shared
+    constexpr bool TWO_ROW = (K == 5 && RV_MEDIAN5_2ROW) || (K == 3 && RV_MEDIAN3_2ROW);
+    if constexpr (TWO_ROW) {
+        // two vertically adjacent output rows per task (slots s, s+1): the K-1 middle window rows are shared
         constexpr int NSLOT = S::NSLOT;
-        constexpr int M = RV_MEDIAN5X2_M;
+        constexpr int M = (K == 5) ? RV_MEDIAN5X2_M : RV_MEDIAN3X2_M;
         constexpr int NG = TILE_W / M;
-        constexpr int NC = M + 4;
+        constexpr int NC = M + K - 1;
+        constexpr int NR = K + 1;                    // plane rows per task
+        constexpr int C0 = LPAD - R;                 // first needed plane word, relative to the group's first output
         static_assert((M == 4 || M == 6) && TILE_W % M == 0 && HALF % 2 == 0, "two-row median layout");
         for (int task = tid; task < 3 * NG * (HALF / 2); task += CHAIN_THREADS) {
             const int m = task % NG;
@@ -858,30 +863,36 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             const int c = t2 % 3, s = 2 * (t2 / 3);
             if (x0 + M * m >= g.W) continue;
             if (y0 + s >= g.H) continue;
-            uint32_t v[NC][6];
+            uint32_t v[NC][NR];
             const uint32_t *pc = P + (c * NSLOT + s) * P_STRIDE;
             if constexpr (M == 4) {
 #pragma unroll
-                for (int d = 0; d < 6; ++d) {
+                for (int d = 0; d < NR; ++d) {
                     const uint4 *p4 = reinterpret_cast<const uint4 *>(pc + d * P_STRIDE + 4 * m);
                     const uint4 q0 = p4[0], q1 = p4[1], q2 = p4[2];
                     const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
-                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[LPAD - R + cc];
+                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[C0 + cc];
                 }
-            } else {
+            } else if constexpr (C0 % 2 == 0 && NC % 2 == 0) {
 #pragma unroll
-                for (int d = 0; d < 6; ++d) {
-                    const uint2 *p2 = reinterpret_cast<const uint2 *>(pc + d * P_STRIDE + M * m + LPAD - R);
+                for (int d = 0; d < NR; ++d) {
+                    const uint2 *p2 = reinterpret_cast<const uint2 *>(pc + d * P_STRIDE + M * m + C0);
 #pragma unroll
                     for (int cc = 0; cc < NC / 2; ++cc) {
                         const uint2 q = p2[cc];
                         v[2 * cc][d] = q.x; v[2 * cc + 1][d] = q.y;
                     }
                 }
+            } else {
+#pragma unroll
+                for (int d = 0; d < NR; ++d)
+#pragma unroll
+                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = pc[d * P_STRIDE + M * m + C0 + cc];
             }
             uint32_t out[2][M];
-            rv_median5x2_net(v, out);
+            if constexpr (K == 5) rv_median5x2_net(v, out);
+            else rv_median3x2_net(v, out);
 #pragma unroll
             for (int hrow = 0; hrow < 2; ++hrow) {
                 uint8_t *o0 = O + (s + hrow) * O_STRIDE + 3 * M * m + c;
@@ -894,9 +905,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             }
         }
         __syncthreads();
-    } else
-#endif
-    if constexpr (K > 0) {
+    } else if constexpr (K > 0) {
         constexpr int NSLOT = S::NSLOT;
         constexpr int M = MedianCfg<K>::M;
         constexpr int NG = TILE_W / M;               // output groups per row

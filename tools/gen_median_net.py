@@ -338,6 +338,51 @@ def build5_2rows(M, parity, rparity=0):
     return d, inp, outs
 
 
+def build3_2rows(M, parity):
+    """3x3, two vertically adjacent output rows per call (window rows 0..2 and 1..3 of four input rows): the two shared
+    rows of every column are ordered once, each output row inserts its own outer element (merge(1,2)), then the
+    pairs scheme: P(a) = ranks 1..4 of two merged columns, median = 4th smallest of P(a) u the third column."""
+    k = 3
+    d = Dag()
+    ncol = M + 2
+    inp = [[d.inp((c, r)) for r in range(4)] for c in range(ncol)]
+    mid = [d.sort([inp[c][1], inp[c][2]]) for c in range(ncol)]
+    rows = [[d.merge([inp[c][0]], mid[c]) for c in range(ncol)], [d.merge([inp[c][3]], mid[c]) for c in range(ncol)]]
+    outs = []
+    for cols in rows:
+        P = {}
+
+        def pair(a, cols=cols, P=P):
+            if a not in P:
+                m = d.merge(cols[a], cols[a + 1])
+                P[a] = m[1:5]                      # ranks that can still be the median of 9 (target rank 4, 3 more elements)
+            return P[a]
+        for o in range(M):
+            acc, single = (pair(o), cols[o + 2]) if o % 2 == parity else (pair(o + 1), cols[o])
+            outs.append(d.kth2(acc, single, 4))    # 4 - 1 discarded below = 3 -> 4th smallest (1-based)
+    return d, inp, outs
+
+
+def verify_2rows_generic(d, inp, outs, k, M, zero_one=True, trials=20000):
+    rng = np.random.RandomState(2)
+    ncol = M + k - 1
+    data = rng.randint(0, 256, (ncol, k + 1, trials)).astype(np.int32)
+    data[:, :, : trials // 2] //= 64
+    vals = {inp[c][r]: data[c, r] for c in range(ncol) for r in range(k + 1)}
+    got = evaluate(d, inp, outs, vals)
+    for half in range(2):
+        for o in range(M):
+            want = np.sort(data[o:o + k, half:half + k].reshape(k * k, trials), axis=0)[(k * k) // 2]
+            if not np.array_equal(got[half * M + o], want):
+                return False
+    if zero_one:
+        for half in range(2):
+            sub = [[inp[c][half + r] for r in range(k)] for c in range(ncol)]
+            if not verify_zero_one(d, sub, outs[half * M:(half + 1) * M], k, M):
+                return False
+    return True
+
+
 def verify_2rows(d, inp, outs, M, zero_one=True, trials=20000):
     rng = np.random.RandomState(1)
     ncol = M + 4
@@ -360,21 +405,21 @@ def verify_2rows(d, inp, outs, M, zero_one=True, trials=20000):
     return True
 
 
-def emit_2rows(d, inp, outs, M, fh):
+def emit_2rows(d, inp, outs, M, fh, k=5):
     live = d.live(outs)
     order = sorted(live)
     nops = sum(1 for n in order if d.nodes[n][0] != "in")
-    ncol = M + 4
+    ncol = M + k - 1
     partner = {}
     for n in order:
         op, a, b = d.nodes[n]
         if op == "min" and ("max", a, b) in d.memo and d.memo[("max", a, b)] in live:
             partner[n] = d.memo[("max", a, b)]
             partner[d.memo[("max", a, b)]] = n
-    fh.write(f"/* k=5, two output rows per call: 2 x {M} outputs from {ncol} columns x 6 rows; {nops} packed min/max ops "
+    fh.write(f"/* k={k}, two output rows per call: 2 x {M} outputs from {ncol} columns x {k + 1} rows; {nops} packed min/max ops "
              f"({nops / (2 * M):.1f} per output pair-lane), {len(partner) // 2} full compare-exchanges */\n")
-    fh.write(f"#define RV_MEDIAN5X2_M {M}\n#define RV_MEDIAN5X2_OPS {nops}\n")
-    fh.write(f"__device__ __forceinline__ void rv_median5x2_net(const uint32_t (&v)[{ncol}][6], uint32_t (&out)[2][{M}])\n{{\n")
+    fh.write(f"#define RV_MEDIAN{k}X2_M {M}\n#define RV_MEDIAN{k}X2_OPS {nops}\n")
+    fh.write(f"__device__ __forceinline__ void rv_median{k}x2_net(const uint32_t (&v)[{ncol}][{k + 1}], uint32_t (&out)[2][{M}])\n{{\n")
     name, done, ce = {}, set(), 0
     for n in order:
         op, a, b = d.nodes[n]
@@ -386,7 +431,7 @@ def emit_2rows(d, inp, outs, M, fh):
         if n in partner:
             lo, hi = (n, partner[n]) if op == "min" else (partner[n], n)
             name[lo], name[hi] = f"t{lo}", f"t{hi}"
-            fh.write(f"    RV_CEX5X2({ce}, t{lo}, t{hi}, {name[a]}, {name[b]});\n")
+            fh.write(f"    RV_CEX{k}X2({ce}, t{lo}, t{hi}, {name[a]}, {name[b]});\n")
             done.update((lo, hi))
             ce += 1
         else:
@@ -538,7 +583,7 @@ def main():
                  "/* per-network compare-exchange macros (the kernel may give each network its own ALU/FMA mix) */\n"
                  "#ifndef RV_CEX3\n#define RV_CEX3 RV_CEX\n#endif\n#ifndef RV_CEX5\n#define RV_CEX5 RV_CEX\n#endif\n"
                  "#ifndef RV_CEX7\n#define RV_CEX7 RV_CEX\n#endif\n#ifndef RV_CEX9\n#define RV_CEX9 RV_CEX\n#endif\n"
-                 "#ifndef RV_CEX5X2\n#define RV_CEX5X2 RV_CEX\n#endif\n\n")
+                 "#ifndef RV_CEX5X2\n#define RV_CEX5X2 RV_CEX\n#endif\n#ifndef RV_CEX3X2\n#define RV_CEX3X2 RV_CEX\n#endif\n\n")
         for k, M in CONFIG.items():
             best = None
             for strat, parity in (("pairs", 0), ("pairs", 1), ("flat", 0), ("quads", 0), ("quads", 1), ("hier", 0), ("hier", 1)):
@@ -575,6 +620,17 @@ def main():
         assert verify_2rows(d, inp, outs, M2, zero_one=not quick), "k=5 two-row network failed verification"
         emit_2rows(d, inp, outs, M2, fh)
         print(f"k=5 two rows M={M2} parity={parity}/{rpar}: {nops} ops ({nops / (2 * M2):.1f}/output), zero-one={'skipped' if quick else True}")
+        M3 = int(os.environ.get("RV_MEDIAN3X2_M", "6"))
+        best = None
+        for parity in (0, 1):
+            d, inp, outs = build3_2rows(M3, parity)
+            nops = sum(1 for n in d.live(outs) if d.nodes[n][0] != "in")
+            if best is None or nops < best[0]:
+                best = (nops, parity, d, inp, outs)
+        nops, parity, d, inp, outs = best
+        assert verify_2rows_generic(d, inp, outs, 3, M3, zero_one=not quick), "k=3 two-row network failed verification"
+        emit_2rows(d, inp, outs, M3, fh, k=3)
+        print(f"k=3 two rows M={M3} parity={parity}: {nops} ops ({nops / (2 * M3):.1f}/output), zero-one={'skipped' if quick else True}")
         fh.write("#endif\n")
     print("wrote", path)
 
