@@ -685,7 +685,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
         }
         if (MODE == 1) copy_lab_tabs(const_cast<LabTabs *>(tabs));
     }
-    if (a.use_tma) mbar_wait(&tma_bar, 0);
+    if (a.use_tma && warp == 0) mbar_wait(&tma_bar, 0);     // one warp polls the mbarrier; the others sleep in the barrier below
     __syncthreads();
 
     // ---- phase 1: CLAHE on the luminance of every staged pixel (or plain unpack when MODE == 2)
