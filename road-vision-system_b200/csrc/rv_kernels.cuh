@@ -97,6 +97,14 @@ __device__ LabTabs g_lab;   // filled once per context from rv_lab_tables.h
 
 __device__ __forceinline__ int sat8(int v) { return min(max(v, 0), 255); }
 
+// A.1 luminance straight from the packed pixel word (B, G, R, x): Y = (1868 B + 9617 G + 4899 R + 8192) >> 14 as two
+// chained 16-bit x 8-bit dot products (IDP.2A.LO takes bytes 0,1, IDP.2A.HI bytes 2,3; the x byte meets a zero coefficient)
+__device__ __forceinline__ uint32_t luma_y(uint32_t px)
+{
+    constexpr uint32_t CBG = 1868u | (9617u << 16), CR0 = 4899u;
+    return __dp2a_hi(CR0, px, __dp2a_lo(CBG, px, 8192u)) >> 14;
+}
+
 // A.1 forward
 __device__ __forceinline__ void ycrcb_fwd(int B, int G, int R, int &Y, int &Cr, int &Cb)
 {
@@ -234,7 +242,6 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
         const int gpr = g.tw >> 4;
         const int total = nrows * gpr;
         const float inv_gpr = 1.0f / (float)gpr;
-        constexpr uint32_t LO = 76u | (145u << 8) | (35u << 16), HI = 7u | (37u << 8) | (19u << 16);
         auto load = [&](int idx, uint4 (&w)[3]) {
             int r = __float2int_rz(__int2float_rn(idx) * inv_gpr);
             int gx = idx - r * gpr;
@@ -246,10 +253,7 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
         auto quad = [&](uint32_t w0, uint32_t w1, uint32_t w2) {
             const uint32_t pp[4] = {w0, __funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 16), w2 >> 8};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t v = (__dp4a(pp[j], LO, 8192u) + (__dp4a(pp[j], HI, 0u) << 8)) >> 14;
-                atomicAdd(&myh[v], 1u);
-            }
+            for (int j = 0; j < 4; ++j) atomicAdd(&myh[luma_y(pp[j])], 1u);
         };
         auto consume = [&](const uint4 (&w)[3]) {
             quad(w[0].x, w[0].y, w[0].z);
@@ -284,16 +288,11 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
         auto process = [&](uint32_t w0, uint32_t w1, uint32_t w2, int y, int x) {
 #if RV_HIST_DP4A
             if (SPACE == 0 && !EXTRA) {
-                // Y = (4899 R + 9617 G + 1868 B + 8192) >> 14 as two byte dot products per pixel on the packed BGRx word
-                // (coefficients split into low and high bytes), no per-channel unpacking
+                // Y straight from the packed BGRx word (luma_y), no per-channel unpacking
                 const uint32_t p0 = w0, p1 = __funnelshift_r(w0, w1, 24), p2 = __funnelshift_r(w1, w2, 16), p3 = w2 >> 8;
-                constexpr uint32_t LO = 76u | (145u << 8) | (35u << 16), HI = 7u | (37u << 8) | (19u << 16);
                 const uint32_t pp[4] = {p0, p1, p2, p3};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t v = (__dp4a(pp[j], LO, 8192u) + (__dp4a(pp[j], HI, 0u) << 8)) >> 14;
-                    atomicAdd(&myh[v], 1u);
-                }
+                for (int j = 0; j < 4; ++j) atomicAdd(&myh[luma_y(pp[j])], 1u);
                 return;
             }
 #endif
@@ -663,9 +662,13 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
         q_smem = nq <= MAXQ;
         const uint32_t *qf = a.quads + (size_t)f * (g.grid + 1) * (g.grid + 1) * 256;
         if (q_smem) {
+            // lq / nqx without an integer division: lq < nq <= MAXQ = 6, so (lq * ceil(256 / nqx)) >> 8 is exact
+            const int rcp_b = (int)((0x2B3440568000ull >> (8 * (nqx - 1))) & 0xFF);   // ceil(256 / nqx) for nqx = 2..6; 0 for 1
+            const int rcp = rcp_b ? rcp_b : 256;
             for (int i = tid; i < nq * 64; i += CHAIN_THREADS) {   // 64 x 16 bytes per quad table
                 const int lq = i >> 6, v4 = i & 63;
-                const int qy = qy_lo + lq / nqx, qx = qx_lo + lq % nqx;
+                const int dq = (lq * rcp) >> 8;
+                const int qy = qy_lo + dq, qx = qx_lo + lq - dq * nqx;
                 reinterpret_cast<uint4 *>(Qs)[i] = __ldg(reinterpret_cast<const uint4 *>(qf + ((size_t)qy * (g.grid + 1) + qx) * 256) + v4);
             }
         }
@@ -743,9 +746,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             } else {
                 // A.1 forward.  Over all 2^24 colours Cb never leaves [1,255] and Cr never goes below 0
                 // (tests/test_oracle.py::test_ycrcb_forward_ranges), so only Cr's upper bound needs a clamp.
-                // Y = (4899 R + 9617 G + 1868 B + 8192) >> 14 as two byte dot products on the packed pixel word
-                constexpr uint32_t LO = 76u | (145u << 8) | (35u << 16), HI = 7u | (37u << 8) | (19u << 16);
-                L = (int)((__dp4a(px[j], LO, 8192u) + (__dp4a(px[j], HI, 0u) << 8)) >> 14);
+                L = (int)luma_y(px[j]);
                 c1 = min(((Rv[j] - L) * 11682 + ((128 << 14) + 8192)) >> 14, 255);
                 c2 = ((Bv[j] - L) * 9241 + ((128 << 14) + 8192)) >> 14;
             }
