@@ -66,6 +66,23 @@ struct rv_ctx {
 
 namespace {
 
+// Chroma round-trip tables of k_chain (layout: rv_kernels.cuh, YccTabs).  Same integer formulas as A.1.
+void build_ycc_table(YccTabs &y)
+{
+    memset(&y, 0, sizeof y);
+    auto clamp8 = [](int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); };
+    for (int i = 0; i <= 510; ++i) {
+        const int d = i - 255;
+        // >> on negative ints is arithmetic here (gcc/nvcc host), as in the oracle
+        const int cb = clamp8((d * 9241 + ((128 << 14) + 8192)) >> 14) - 128;
+        const int cr = clamp8((d * 11682 + ((128 << 14) + 8192)) >> 14) - 128;
+        const int fB = (cb * 29049 + 8192) >> 14, fR = (cr * 22987 + 8192) >> 14;
+        const int tB = cb * -5636 / 2, tR = cr * -11698 / 2 + 4096 + (1 << 21);      // both products are even
+        y.e[i] = ((uint32_t)tB << 10) + (uint32_t)(fB + 256);
+        y.e[512 + i] = ((uint32_t)tR << 10) + (uint32_t)(fR + 256);
+    }
+}
+
 int fail(rv_ctx *c, int code, const char *fmt, ...)
 {
     if (c) {
@@ -663,6 +680,11 @@ int rv_create(int device, rv_ctx **out)
     cudaError_t e = cudaMemcpyToSymbol(g_lab, t, sizeof *t);
     delete t;
     if (e != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
+    {
+        YccTabs y;
+        build_ycc_table(y);
+        if (cudaMemcpyToSymbol(g_ycc, &y, sizeof y) != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
+    }
     *out = ctx;
     return RV_OK;
 }

@@ -95,6 +95,16 @@ struct LabTabs {
 static_assert(sizeof(LabTabs) % 16 == 0, "LabTabs must be 16-byte granular");
 __device__ LabTabs g_lab;   // filled once per context from rv_lab_tables.h
 
+// YCrCb chroma round trip (A.1) as two 511-entry tables indexed by d + 255, d = B - Y (first 512 words) or R - Y (next 512).
+// Cb and Cr only pass through the CLAHE, so B' = Y' + fB(d_B), R' = Y' + fR(d_R) and G' = Y' + ((tB + tR + 8192) >> 14) with
+//   fB = ((Cb - 128) * 29049 + 8192) >> 14,  tB = (Cb - 128) * -5636   (Cb = sat8((d * 9241 + (128 << 14) + 8192) >> 14)),
+//   fR = ((Cr - 128) * 22987 + 8192) >> 14,  tR = (Cr - 128) * -11698  (Cr likewise with 11682);  tB, tR and 8192 are even.
+// Entry: bits 0..9 = f + 256 (two of them never carry into bit 10), bits 10..31 = t / 2 (+ 4096 + 2^21 in the R table, so
+// that the sum of the two fields is non-negative): (eB + eR) >> 23 == 256 + ((tB + tR + 8192) >> 14).  Built on the host
+// (rv_b200.cu: build_ycc_table) with the same integer formulas.
+struct YccTabs { uint32_t e[1024]; };
+__device__ YccTabs g_ycc;
+
 __device__ __forceinline__ int sat8(int v) { return min(max(v, 0), 255); }
 
 // A.1 luminance straight from the packed pixel word (B, G, R, x): Y = (1868 B + 9617 G + 4899 R + 8192) >> 14 as two
@@ -552,7 +562,7 @@ struct ChainSmem {
     static constexpr size_t p_bytes = K > 0 ? (size_t)3 * NSLOT * P_STRIDE * 4 : (size_t)TILE_H * O_STRIDE;  // K==0: output staging
     static constexpr size_t row_bytes = (size_t)BOX_H * 16;
     static constexpr size_t q_bytes = MODE == 2 ? 0 : (size_t)MAXQ * 256 * 4;
-    static constexpr size_t t_bytes = MODE == 1 ? sizeof(LabTabs) : 0;
+    static constexpr size_t t_bytes = MODE == 1 ? sizeof(LabTabs) : (MODE == 0 && K > 0) ? sizeof(YccTabs) : 0;
     static constexpr size_t off_a = 0;
     static constexpr size_t off_p = (a_bytes + 15) & ~(size_t)15;
     static constexpr size_t off_row = off_p + ((p_bytes + 15) & ~(size_t)15);
@@ -687,6 +697,11 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
                                    __int_as_float((gy - (y0 - R)) * A_STRIDE));
         }
         if (MODE == 1) copy_lab_tabs(const_cast<LabTabs *>(tabs));
+        if (MODE == 0 && K > 0) {
+            const uint4 *ys = reinterpret_cast<const uint4 *>(&g_ycc);
+            uint4 *yd = reinterpret_cast<uint4 *>(smem + S::off_t);
+            for (int i = tid; i < (int)(sizeof(YccTabs) / 16); i += CHAIN_THREADS) yd[i] = __ldg(ys + i);
+        }
     }
     if (a.use_tma && warp == 0) mbar_wait(&tma_bar, 0);     // one warp polls the mbarrier; the others sleep in the barrier below
     __syncthreads();
@@ -696,6 +711,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
     // YCrCb results are produced UNCLAMPED with RV_BIAS16 added (K > 0): the saturation to [0,255] happens on the
     // packed u16x2 plane words (two values per VIMNMX.S16x2) instead of per value; LAB / passthrough values are exact.
     constexpr bool RAW = (MODE == 0) && (K > 0);
+    const uint32_t *ycc = reinterpret_cast<const uint32_t *>(smem + S::off_t);   // chroma tables (RAW only)
     // phase 1 is instantiated twice (quad tables in shared memory / fetched from global) and the CTA-uniform choice is
     // made once, outside: a predicated dual path costs issue slots for every masked-off address instruction.
     auto phase1 = [&](auto QS) {
@@ -740,9 +756,16 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
         const int qrow = __float_as_int(rp.z);                    // (local quad row * quads per row) << 8, or the global row
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int L, c1, c2;
+            int L, c1 = 0, c2 = 0;
+            uint32_t eB = 0, eR = 0;
             if (MODE == 1) {
                 lab_fwd(tabs, Bv[j], Gv[j], Rv[j], L, c1, c2);
+            } else if constexpr (RAW) {
+                // chroma round trip from the tables (see YccTabs): entries of d = B - Y and d = R - Y
+                L = (int)luma_y(px[j]);
+                const uint32_t *yrow = ycc + (255 - L);
+                eB = yrow[Bv[j]];
+                eR = yrow[512 + Rv[j]];
             } else {
                 // A.1 forward.  Over all 2^24 colours Cb never leaves [1,255] and Cr never goes below 0
                 // (tests/test_oracle.py::test_ycrcb_forward_ranges), so only Cr's upper bound needs a clamp.
@@ -769,17 +792,21 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             // round-half-even via the 1.5*2^23 trick; res <= 255*(1 + 1e-6), so the result is already in [0,255]
             // RAW: the bias 0x6400 rides along in the magic constant and the float's upper bits are left in place; only the
             // low 16 bits of the sums below are ever used (pack2 keeps the low halves), so no masking is needed.
-            const int L2 = RAW ? __float_as_int(__fadd_rn(res, 12582912.0f + 25600.0f))
+            // (25600 - 256: the tables' f fields carry + 256)
+            const int L2 = RAW ? __float_as_int(__fadd_rn(res, 12582912.0f + 25600.0f - 256.0f))
                                : (__float_as_int(__fadd_rn(res, 12582912.0f)) & 0x1FF);
             if (MODE == 1) {
                 lab_inv_args(tabs, L2, c1, c2, ly[j], lx[j], lz[j]);
+            } else if constexpr (RAW) {
+                o[j] = L2 + (int)(eB & 0x3FFu);
+                o[4 + j] = L2 + (int)((eB + eR) >> 23);
+                o[8 + j] = L2 + (int)(eR & 0x3FFu);
             } else {
                 // A.1 inverse with the -128 offsets folded into the rounding constants
                 const int bb = L2 + ((c2 * 29049 + (8192 - 128 * 29049)) >> 14);
                 const int gg = L2 + ((c2 * -5636 + c1 * -11698 + (8192 + 128 * (5636 + 11698))) >> 14);
                 const int rr = L2 + ((c1 * 22987 + (8192 - 128 * 22987)) >> 14);
-                if (RAW) { o[j] = bb; o[4 + j] = gg; o[8 + j] = rr; }
-                else { o[j] = sat8(bb); o[4 + j] = sat8(gg); o[8 + j] = sat8(rr); }
+                o[j] = sat8(bb); o[4 + j] = sat8(gg); o[8 + j] = sat8(rr);
             }
         }
         if (MODE == 1) {
