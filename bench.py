@@ -360,6 +360,17 @@ def run_gpu(args, rank, world, local_rank):
                      "whole_chain_achieved_gbs": ALGO_BYTES_PER_FRAME * value / world / 1e9,
                      "traffic": TRAFFIC_NCU},
     })
+    # why the HBM fraction is low: k_chain is bound by instruction issue, not by memory.  Warp instructions
+    # per launch come from the committed ncu capture, the launch time is the live measurement above.
+    sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    issue_peak = sms * 4 * sm_clock * 1e6                      # one warp instruction per scheduler per clock
+    line["roofline"]["issue"] = {
+        "warp_instr_per_launch": WARP_INSTR_NCU * frames_per_launch / 64.0, "thread_instr_per_pixel": WARP_INSTR_NCU * 32 / (64.0 * H * W),
+        "achieved_gwarp_instr_s": WARP_INSTR_NCU * frames_per_launch / 64.0 / avg_launch_s / 1e9 if chain_n else None,
+        "peak_gwarp_instr_s": issue_peak / 1e9,
+        "frac": (WARP_INSTR_NCU * frames_per_launch / 64.0 / avg_launch_s / issue_peak) if chain_n else None,
+        "source": "smsp__inst_executed.sum of one k_chain launch (profiles/r1_v8_k_chain_summary.txt); peak = SMs x 4 schedulers x SM clock"}
     if world == 1 and not args.no_cpu:
         fps_p, cores_p, n_p = cpu_chain_fps(list(pool), 6.0, "procs")
         from oracle import cv2_chain            # the CPU leg doubles as the checker: never report a wrong kernel's speed
@@ -377,9 +388,11 @@ def run_gpu(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
-# DRAM bytes of one k_chain launch (64 x 1080p frames: dram__bytes_read.sum 403.5 MB + dram__bytes_write.sum 355.0 MB) from the
-# committed `ncu --set full` capture profiles/r1_v6_k_chain_summary.txt; algorithmic bytes of that launch: 796.3 MB
-TRAFFIC_NCU = 758.6e6
+# DRAM bytes of one k_chain launch (64 x 1080p frames: dram__bytes_read.sum 404.2 MB + dram__bytes_write.sum 356.3 MB) and its
+# executed warp instructions, from the committed `ncu --set full` capture profiles/r1_v8_k_chain_summary.txt; algorithmic
+# bytes of that launch: 796.3 MB
+TRAFFIC_NCU = 760.5e6
+WARP_INSTR_NCU = 808966144
 
 
 def main():

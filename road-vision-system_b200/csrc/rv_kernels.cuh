@@ -562,7 +562,7 @@ struct ChainSmem {
     static constexpr size_t p_bytes = K > 0 ? (size_t)3 * NSLOT * P_STRIDE * 4 : (size_t)TILE_H * O_STRIDE;  // K==0: output staging
     static constexpr size_t row_bytes = (size_t)BOX_H * 16;
     static constexpr size_t q_bytes = MODE == 2 ? 0 : (size_t)MAXQ * 256 * 4;
-    static constexpr size_t t_bytes = MODE == 1 ? sizeof(LabTabs) : (MODE == 0 && K > 0) ? sizeof(YccTabs) : 0;
+    static constexpr size_t t_bytes = MODE == 1 ? sizeof(LabTabs) : MODE == 0 ? sizeof(YccTabs) : 0;
     static constexpr size_t off_a = 0;
     static constexpr size_t off_p = (a_bytes + 15) & ~(size_t)15;
     static constexpr size_t off_row = off_p + ((p_bytes + 15) & ~(size_t)15);
@@ -697,7 +697,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
                                    __int_as_float((gy - (y0 - R)) * A_STRIDE));
         }
         if (MODE == 1) copy_lab_tabs(const_cast<LabTabs *>(tabs));
-        if (MODE == 0 && K > 0) {
+        if (MODE == 0) {
             const uint4 *ys = reinterpret_cast<const uint4 *>(&g_ycc);
             uint4 *yd = reinterpret_cast<uint4 *>(smem + S::off_t);
             for (int i = tid; i < (int)(sizeof(YccTabs) / 16); i += CHAIN_THREADS) yd[i] = __ldg(ys + i);
@@ -760,18 +760,13 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             uint32_t eB = 0, eR = 0;
             if (MODE == 1) {
                 lab_fwd(tabs, Bv[j], Gv[j], Rv[j], L, c1, c2);
-            } else if constexpr (RAW) {
-                // chroma round trip from the tables (see YccTabs): entries of d = B - Y and d = R - Y
+            } else {
+                // A.1 forward: Y from the packed pixel word; the chroma round trip comes from the tables (see YccTabs):
+                // entries of d = B - Y and d = R - Y
                 L = (int)luma_y(px[j]);
                 const uint32_t *yrow = ycc + (255 - L);
                 eB = yrow[Bv[j]];
                 eR = yrow[512 + Rv[j]];
-            } else {
-                // A.1 forward.  Over all 2^24 colours Cb never leaves [1,255] and Cr never goes below 0
-                // (tests/test_oracle.py::test_ycrcb_forward_ranges), so only Cr's upper bound needs a clamp.
-                L = (int)luma_y(px[j]);
-                c1 = min(((Rv[j] - L) * 11682 + ((128 << 14) + 8192)) >> 14, 255);
-                c2 = ((Bv[j] - L) * 9241 + ((128 << 14) + 8192)) >> 14;
             }
             uint32_t q;
             if constexpr (q_in_smem) q = Qs[qrow + qcol[j] + L];
@@ -792,21 +787,19 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             // round-half-even via the 1.5*2^23 trick; res <= 255*(1 + 1e-6), so the result is already in [0,255]
             // RAW: the bias 0x6400 rides along in the magic constant and the float's upper bits are left in place; only the
             // low 16 bits of the sums below are ever used (pack2 keeps the low halves), so no masking is needed.
-            // (25600 - 256: the tables' f fields carry + 256)
-            const int L2 = RAW ? __float_as_int(__fadd_rn(res, 12582912.0f + 25600.0f - 256.0f))
-                               : (__float_as_int(__fadd_rn(res, 12582912.0f)) & 0x1FF);
+            // YCrCb: - 256 because the tables' f fields and the G sum carry + 256.
+            constexpr float MAGIC = 12582912.0f + (RAW ? 25600.0f : 0.0f) - (MODE == 0 ? 256.0f : 0.0f);
+            const int Lw = __float_as_int(__fadd_rn(res, MAGIC));
             if (MODE == 1) {
-                lab_inv_args(tabs, L2, c1, c2, ly[j], lx[j], lz[j]);
-            } else if constexpr (RAW) {
-                o[j] = L2 + (int)(eB & 0x3FFu);
-                o[4 + j] = L2 + (int)((eB + eR) >> 23);
-                o[8 + j] = L2 + (int)(eR & 0x3FFu);
+                lab_inv_args(tabs, Lw & 0x1FF, c1, c2, ly[j], lx[j], lz[j]);
             } else {
-                // A.1 inverse with the -128 offsets folded into the rounding constants
-                const int bb = L2 + ((c2 * 29049 + (8192 - 128 * 29049)) >> 14);
-                const int gg = L2 + ((c2 * -5636 + c1 * -11698 + (8192 + 128 * (5636 + 11698))) >> 14);
-                const int rr = L2 + ((c1 * 22987 + (8192 - 128 * 22987)) >> 14);
-                o[j] = sat8(bb); o[4 + j] = sat8(gg); o[8 + j] = sat8(rr);
+                // A.1 inverse: B' = Y' + fB, G' = Y' + ((tB + tR + 8192) >> 14), R' = Y' + fR
+                const int L2 = RAW ? Lw : (Lw << 16) >> 16;          // non-RAW: sign-extended Y' - 256
+                const int bb = L2 + (int)(eB & 0x3FFu);
+                const int gg = L2 + (int)((eB + eR) >> 23);
+                const int rr = L2 + (int)(eR & 0x3FFu);
+                if (RAW) { o[j] = bb; o[4 + j] = gg; o[8 + j] = rr; }
+                else { o[j] = sat8(bb); o[4 + j] = sat8(gg); o[8 + j] = sat8(rr); }
             }
         }
         if (MODE == 1) {
