@@ -78,8 +78,8 @@ void build_ycc_table(YccTabs &y)
         const int cr = clamp8((d * 11682 + ((128 << 14) + 8192)) >> 14) - 128;
         const int fB = (cb * 29049 + 8192) >> 14, fR = (cr * 22987 + 8192) >> 14;
         const int tB = cb * -5636 / 2, tR = cr * -11698 / 2 + 4096 + (1 << 21);      // both products are even
-        y.e[i] = ((uint32_t)tB << 10) + (uint32_t)(fB + 256);
-        y.e[512 + i] = ((uint32_t)tR << 10) + (uint32_t)(fR + 256);
+        y.e[i] = ((uint32_t)(fB + 256) << 22) | ((uint32_t)tB & 0x3FFFFFu);
+        y.e[512 + i] = ((uint32_t)(fR + 256) << 22) | ((uint32_t)tR & 0x3FFFFFu);
     }
 }
 

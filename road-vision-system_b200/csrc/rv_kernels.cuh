@@ -99,9 +99,9 @@ __device__ LabTabs g_lab;   // filled once per context from rv_lab_tables.h
 // Cb and Cr only pass through the CLAHE, so B' = Y' + fB(d_B), R' = Y' + fR(d_R) and G' = Y' + ((tB + tR + 8192) >> 14) with
 //   fB = ((Cb - 128) * 29049 + 8192) >> 14,  tB = (Cb - 128) * -5636   (Cb = sat8((d * 9241 + (128 << 14) + 8192) >> 14)),
 //   fR = ((Cr - 128) * 22987 + 8192) >> 14,  tR = (Cr - 128) * -11698  (Cr likewise with 11682);  tB, tR and 8192 are even.
-// Entry: bits 0..9 = f + 256 (two of them never carry into bit 10), bits 10..31 = t / 2 (+ 4096 + 2^21 in the R table, so
-// that the sum of the two fields is non-negative): (eB + eR) >> 23 == 256 + ((tB + tR + 8192) >> 14).  Built on the host
-// (rv_b200.cu: build_ycc_table) with the same integer formulas.
+// Entry: bits 22..31 = f + 256, bits 0..21 = t / 2 modulo 2^22 (+ 4096 + 2^21 in the R table, so that the sum of the two
+// fields lies in [0, 2^22)): ((eB + eR) << 10) >> 23 == 256 + ((tB + tR + 8192) >> 14), e >> 22 == f + 256 -- a shift-and-add
+// (LEA.HI) per channel.  Built on the host (rv_b200.cu: build_ycc_table) with the same integer formulas.
 struct YccTabs { uint32_t e[1024]; };
 __device__ YccTabs g_ycc;
 
@@ -711,7 +711,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
     // YCrCb results are produced UNCLAMPED with RV_BIAS16 added (K > 0): the saturation to [0,255] happens on the
     // packed u16x2 plane words (two values per VIMNMX.S16x2) instead of per value; LAB / passthrough values are exact.
     constexpr bool RAW = (MODE == 0) && (K > 0);
-    const uint32_t *ycc = reinterpret_cast<const uint32_t *>(smem + S::off_t);   // chroma tables (RAW only)
+    const uint32_t ycc_s = smem_u32(smem + S::off_t);            // shared-memory address of the chroma tables (MODE 0)
     // phase 1 is instantiated twice (quad tables in shared memory / fetched from global) and the CTA-uniform choice is
     // made once, outside: a predicated dual path costs issue slots for every masked-off address instruction.
     auto phase1 = [&](auto QS) {
@@ -764,9 +764,13 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
                 // A.1 forward: Y from the packed pixel word; the chroma round trip comes from the tables (see YccTabs):
                 // entries of d = B - Y and d = R - Y
                 L = (int)luma_y(px[j]);
-                const uint32_t *yrow = ycc + (255 - L);
-                eB = yrow[Bv[j]];
-                eR = yrow[512 + Rv[j]];
+                // one shared term (table base - 4 Y) for both look-ups; the empty asm keeps the compiler from re-associating it
+                // into a subtraction per channel.  The tables are constant after the barrier above and the address depends on
+                // this pixel, so a plain (non-volatile) shared load is safe.
+                uint32_t yrow = ycc_s + 4u * 255u - 4u * (uint32_t)L;
+                asm("" : "+r"(yrow));
+                asm("ld.shared.u32 %0, [%1];" : "=r"(eB) : "r"(yrow + 4u * (uint32_t)Bv[j]));
+                asm("ld.shared.u32 %0, [%1+2048];" : "=r"(eR) : "r"(yrow + 4u * (uint32_t)Rv[j]));
             }
             uint32_t q;
             if constexpr (q_in_smem) q = Qs[qrow + qcol[j] + L];
@@ -795,9 +799,9 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             } else {
                 // A.1 inverse: B' = Y' + fB, G' = Y' + ((tB + tR + 8192) >> 14), R' = Y' + fR
                 const int L2 = RAW ? Lw : (Lw << 16) >> 16;          // non-RAW: sign-extended Y' - 256
-                const int bb = L2 + (int)(eB & 0x3FFu);
-                const int gg = L2 + (int)((eB + eR) >> 23);
-                const int rr = L2 + (int)(eR & 0x3FFu);
+                const int bb = L2 + (int)(eB >> 22);
+                const int gg = L2 + (int)(((eB + eR) << 10) >> 23);
+                const int rr = L2 + (int)(eR >> 22);
                 if (RAW) { o[j] = bb; o[4 + j] = gg; o[8 + j] = rr; }
                 else { o[j] = sat8(bb); o[4 + j] = sat8(gg); o[8 + j] = sat8(rr); }
             }
