@@ -59,6 +59,7 @@ EXPORTS = {
     # name: (restype, argtypes)
     "rv_version": (C.c_char_p, []),
     "rv_device_count": (C.c_int, []),
+    "rv_ycc_table": (C.c_int, [C.POINTER(C.c_uint32)]),
     "rv_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "rv_destroy": (None, [C.c_void_p]),
     "rv_last_error": (C.c_char_p, [C.c_void_p]),

@@ -636,6 +636,15 @@ extern "C" {
 
 const char *rv_version(void) { return "rv_b200 0.1 (sm_100a)"; }
 
+int rv_ycc_table(uint32_t *out1024)
+{
+    if (!out1024) return RV_ERR_ARG;
+    YccTabs y;
+    build_ycc_table(y);
+    memcpy(out1024, y.e, sizeof y.e);
+    return RV_OK;
+}
+
 int rv_device_count(void)
 {
     int n = 0;

@@ -160,3 +160,29 @@ def test_batch_feeder_order_timestamps_backpressure():
                 feeder.release(h)
             held = []
     assert seen == [i % 5 for i in range(23)]          # nothing dropped, nothing reordered, partial last batch delivered
+
+
+def test_ycc_chroma_table_equals_oracle_round_trip_exhaustive():
+    """k_chain replaces the Cr/Cb arithmetic of BGR2YCrCb / YCrCb2BGR by two look-ups in the table rv_create uploads
+    (include/rv_b200.h: rv_ycc_table).  Host-only check over ALL 2^24 colours, with the new luminance Y' swept against Y:
+    B' = Y' + f(B - Y), G' = Y' + ((tB + tR + 8192) >> 14), R' = Y' + f(R - Y) must equal the oracle's
+    ycrcb2bgr(Y', Cr, Cb) with (Y, Cr, Cb) = bgr2ycrcb(B, G, R)."""
+    import ctypes as C
+    from rvb200 import _native
+    from oracle import rv_oracle as O
+    lib = _native.load_library()
+    tab = np.zeros(1024, np.uint32)
+    assert lib.rv_ycc_table(tab.ctypes.data_as(C.POINTER(C.c_uint32))) == 0
+    v = np.arange(1 << 24, dtype=np.uint32)
+    img = np.stack([v & 255, (v >> 8) & 255, v >> 16], -1).astype(np.uint8).reshape(4096, 4096, 3)
+    ycc = O.bgr2ycrcb(img)
+    Y = ycc[..., 0].astype(np.int64)
+    eB = tab[:512][img[..., 0].astype(np.int64) - Y + 255].astype(np.int64)
+    eR = tab[512:][img[..., 2].astype(np.int64) - Y + 255].astype(np.int64)
+    fB, fR = (eB >> 22) - 256, (eR >> 22) - 256
+    g = ((((eB + eR) & 0xFFFFFFFF) << 10) & 0xFFFFFFFF) >> 23
+    for shift in (0, 1, 37, 128, 255):           # Y' = (Y + shift) mod 256 exercises every (Y', chroma) pairing that matters
+        y2 = (Y + shift) & 255
+        want = O.ycrcb2bgr(np.stack([y2.astype(np.uint8), ycc[..., 1], ycc[..., 2]], -1))
+        got = np.stack([np.clip(y2 + fB, 0, 255), np.clip(y2 + g - 256, 0, 255), np.clip(y2 + fR, 0, 255)], -1).astype(np.uint8)
+        assert np.array_equal(got, want), shift
