@@ -882,18 +882,26 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
         constexpr int NR = K + 1;                    // plane rows per task
         constexpr int C0 = LPAD - R;                 // first needed plane word, relative to the group's first output
         static_assert((M == 4 || M == 6) && TILE_W % M == 0 && HALF % 2 == 0, "two-row median layout");
-        for (int task = tid; task < 3 * NG * (HALF / 2); task += CHAIN_THREADS) {
-            const int m = task % NG;
-            const int t2 = task / NG;
-            const int c = t2 % 3, s = 2 * (t2 / 3);
-            if (x0 + M * m >= g.W) continue;
-            if (y0 + s >= g.H) continue;
+        // task = (row pair sp, channel c, group m), m fastest; a thread's next task is CHAIN_THREADS further on.  The three
+        // coordinates are carried incrementally (one division per thread instead of four per task).
+        constexpr int DM = CHAIN_THREADS % NG, DT = CHAIN_THREADS / NG, DC = DT % 3, DSP = DT / 3;
+        int m = tid % NG, c = (tid / NG) % 3, sp = (tid / NG) / 3;
+        for (; sp < HALF / 2; ) {
+            const int s = 2 * sp;
+            const bool live = (x0 + M * m < g.W) && (y0 + s < g.H);
+            const int mo = m, co = c;
+            // advance to this thread's next task
+            m += DM; c += DC; sp += DSP;
+            if (m >= NG) { m -= NG; ++c; }
+            if (c >= 3) { c -= 3; ++sp; }
+            if constexpr (DC + 1 >= 3) { if (c >= 3) { c -= 3; ++sp; } }
+            if (!live) continue;
             uint32_t v[NC][NR];
-            const uint32_t *pc = P + (c * NSLOT + s) * P_STRIDE;
+            const uint32_t *pc = P + (co * NSLOT + s) * P_STRIDE;
             if constexpr (M == 4) {
 #pragma unroll
                 for (int d = 0; d < NR; ++d) {
-                    const uint4 *p4 = reinterpret_cast<const uint4 *>(pc + d * P_STRIDE + 4 * m);
+                    const uint4 *p4 = reinterpret_cast<const uint4 *>(pc + d * P_STRIDE + 4 * mo);
                     const uint4 q0 = p4[0], q1 = p4[1], q2 = p4[2];
                     const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
@@ -902,7 +910,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             } else if constexpr (C0 % 2 == 0 && NC % 2 == 0) {
 #pragma unroll
                 for (int d = 0; d < NR; ++d) {
-                    const uint2 *p2 = reinterpret_cast<const uint2 *>(pc + d * P_STRIDE + M * m + C0);
+                    const uint2 *p2 = reinterpret_cast<const uint2 *>(pc + d * P_STRIDE + M * mo + C0);
 #pragma unroll
                     for (int cc = 0; cc < NC / 2; ++cc) {
                         const uint2 q = p2[cc];
@@ -913,14 +921,14 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
 #pragma unroll
                 for (int d = 0; d < NR; ++d)
 #pragma unroll
-                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = pc[d * P_STRIDE + M * m + C0 + cc];
+                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = pc[d * P_STRIDE + M * mo + C0 + cc];
             }
             uint32_t out[2][M];
             if constexpr (K == 5) rv_median5x2_net(v, out);
             else rv_median3x2_net(v, out);
 #pragma unroll
             for (int hrow = 0; hrow < 2; ++hrow) {
-                uint8_t *o0 = O + (s + hrow) * O_STRIDE + 3 * M * m + c;
+                uint8_t *o0 = O + (s + hrow) * O_STRIDE + 3 * M * mo + co;
                 uint8_t *o1 = o0 + HALF * O_STRIDE;
 #pragma unroll
                 for (int j = 0; j < M; ++j) {
