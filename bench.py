@@ -255,6 +255,8 @@ def run_gpu(args, rank, world, local_rank):
         ctx.set_option("chunk_frames", args.chunk)
     if args.overlap >= 0:
         ctx.set_option("overlap_groups", args.overlap)
+    if args.prefetch >= 0:
+        ctx.set_option("prefetch_ctas", args.prefetch)
     params = rvb200.Params.make(SPACE, CLIP, GRID, KSIZE)
     pool = make_pool()
     a, _ = shard_range(BATCH * world, rank, world)            # this rank's slab of the global frame index space
@@ -404,6 +406,7 @@ def main():
     ap.add_argument("--group", type=int, default=0, help="frames per hist->lut->chain group (0 = library default)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per host pipeline chunk (0 = library default)")
     ap.add_argument("--overlap", type=int, default=-1, help="groups per batch for the histogram/chain overlap (-1 = library default)")
+    ap.add_argument("--prefetch", type=int, default=-1, help="k_chain L2 prefetch distance in CTAs per SM (-1 = library default, 0 = off)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     args = ap.parse_args()

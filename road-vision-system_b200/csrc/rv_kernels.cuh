@@ -501,6 +501,13 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
                  : "memory");
 }
 
+// L2 prefetch of a box (no shared-memory destination, no barrier): warms the tile a later CTA will stage
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3+K4: fused apply (+ inverse colour) + median.
 // ---------------------------------------------------------------------------------------------
@@ -530,6 +537,8 @@ struct ChainArgs {
     const uint32_t *quads;             // [frames][(grid+1)^2][256]
     const int32_t *flags;              // optional per-frame gate flags (0 = skip frame)
     int use_tma;                       // stage the box with one cp.async.bulk.tensor per CTA (aligned buffers)
+    int prefetch_dist;                 // > 0: also prefetch into L2 the box of the CTA this many linear block ids ahead (the
+                                       // one that takes this CTA's place on the SM), so its staging wait is an L2 hit
     const float *colp;                 // per 4-pixel box group: xa[4], xa1[4], -2^23 xa[4], -2^23 xa1[4], quad column[4]
     // optional fused detector-input stage (integer down-scale letterbox, see k_letterbox): 0 = off
     uint16_t *lb_out;                  // [frames][3][lb_S][lb_S] halves, RGB planes, value/255
@@ -610,6 +619,16 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&tma_bar, (uint32_t)(BOX_H * A_STRIDE));
             tma_load_3d(A, &tmap, &tma_bar, bx0 / 4, y0 - R, f);
+            if (a.prefetch_dist > 0) {
+                const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) + (unsigned)a.prefetch_dist;
+                const unsigned per_frame = gridDim.x * gridDim.y;
+                const unsigned nf = lin / per_frame, rem = lin - nf * per_frame;
+                const unsigned ny = rem / gridDim.x, nx = rem - ny * gridDim.x;
+                if (nf < gridDim.z) {
+                    const int nbx = 3 * ((int)nx * TILE_W - LPAD);
+                    tma_prefetch_3d(&tmap, (nbx - (nbx & 15)) / 4, (int)ny * TILE_H - R, (int)nf);
+                }
+            }
         }
     } else {
         const int rowbytes = 3 * g.W;

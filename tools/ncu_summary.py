@@ -50,6 +50,7 @@ def main():
     body = rows[hidx[0] + 1:end]
     iS, iI, iSm = h.index('Source'), h.index('Instructions Executed'), h.index('# Samples')
     tot, byop, samp, acc, phases = 0, collections.Counter(), collections.Counter(), 0, []
+    ph_inst, ph_samp = [0], [0]          # per phase (code between two BAR.SYNCs): instructions and warp-state samples
     for r in body:
         if len(r) <= iI or not r[iI]:
             continue
@@ -58,10 +59,15 @@ def main():
         op = (toks[1] if toks[0].startswith('@') else toks[0]).split('.')[0]
         byop[op] += n; samp[op] += int(r[iSm] or 0)
         acc += n
+        ph_inst[-1] += n; ph_samp[-1] += int(r[iSm] or 0)
         if op == 'BAR':
             phases.append(acc)
+            ph_inst.append(0); ph_samp.append(0)
     print(f"\nwarp instructions executed: {tot}", file=out)
     print("cumulative share at each BAR.SYNC: " + ", ".join(f"{100 * x / tot:.1f}%" for x in phases), file=out)
+    ts = max(sum(ph_samp), 1)
+    print("per phase, share of instructions / share of sampled warp time (a phase whose time share exceeds its instruction "
+          "share is waiting, not issuing): " + ", ".join(f"{100 * a / tot:.1f}% / {100 * b / ts:.1f}%" for a, b in zip(ph_inst, ph_samp)), file=out)
     for op, n in byop.most_common(22):
         print(f"  {op:12s} {n:12d} {100 * n / tot:5.1f}%   stall samples {samp[op]}", file=out)
 
