@@ -372,7 +372,7 @@ def run_gpu(args, rank, world, local_rank):
         "achieved_gwarp_instr_s": WARP_INSTR_NCU * frames_per_launch / 64.0 / avg_launch_s / 1e9 if chain_n else None,
         "peak_gwarp_instr_s": issue_peak / 1e9,
         "frac": (WARP_INSTR_NCU * frames_per_launch / 64.0 / avg_launch_s / issue_peak) if chain_n else None,
-        "source": "smsp__inst_executed.sum of one k_chain launch (profiles/r1_v8_k_chain_summary.txt); peak = SMs x 4 schedulers x SM clock"}
+        "source": "smsp__inst_executed.sum of one k_chain launch (profiles/r1_v9_k_chain_summary.txt); peak = SMs x 4 schedulers x SM clock"}
     if world == 1 and not args.no_cpu:
         fps_p, cores_p, n_p = cpu_chain_fps(list(pool), 6.0, "procs")
         from oracle import cv2_chain            # the CPU leg doubles as the checker: never report a wrong kernel's speed
@@ -390,11 +390,11 @@ def run_gpu(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
-# DRAM bytes of one k_chain launch (64 x 1080p frames: dram__bytes_read.sum 404.2 MB + dram__bytes_write.sum 356.3 MB) and its
-# executed warp instructions, from the committed `ncu --set full` capture profiles/r1_v8_k_chain_summary.txt; algorithmic
+# DRAM bytes of one k_chain launch (64 x 1080p frames: dram__bytes_read.sum 403.5 MB + dram__bytes_write.sum 356.1 MB) and its
+# executed warp instructions, from the committed `ncu --set full` capture profiles/r1_v9_k_chain_summary.txt; algorithmic
 # bytes of that launch: 796.3 MB
-TRAFFIC_NCU = 760.5e6
-WARP_INSTR_NCU = 808966144
+TRAFFIC_NCU = 759.6e6
+WARP_INSTR_NCU = 782662144
 
 
 def main():
