@@ -71,7 +71,10 @@ __device__ __forceinline__ void rv_ce_fma(uint32_t a, uint32_t b, uint32_t &lo, 
 #endif
 #define RV_CEX3(n, lo, hi, a, b) RV_CEX_MIX(RV_FMA3_NUM, RV_FMA3_DEN, n, lo, hi, a, b)
 
-#include "rv_median_net.h"
+#ifndef RV_MEDIAN_NET_FILE
+#define RV_MEDIAN_NET_FILE "rv_median_net.h"      // tools/exp_median_order.py builds the kernel against alternative emissions
+#endif
+#include RV_MEDIAN_NET_FILE
 
 namespace rv {
 
