@@ -929,15 +929,21 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
 #pragma unroll
                     for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[C0 + cc];
                 }
-            } else if constexpr (C0 % 2 == 0 && NC % 2 == 0) {
+            } else if constexpr (M % 2 == 0) {
+                // 8-byte loads from the even word at or below the first needed column (k = 3: one unused leading word);
+                // with M = 6 the 16 lanes of a phase hit 16 distinct even banks (6m + 2 mod 32): conflict-free
+                constexpr int C0E = C0 & ~1, SKIP = C0 - C0E, NW = (SKIP + NC + 1) / 2;
 #pragma unroll
                 for (int d = 0; d < NR; ++d) {
-                    const uint2 *p2 = reinterpret_cast<const uint2 *>(pc + d * P_STRIDE + M * mo + C0);
+                    const uint2 *p2 = reinterpret_cast<const uint2 *>(pc + d * P_STRIDE + M * mo + C0E);
+                    uint32_t w[2 * NW];
 #pragma unroll
-                    for (int cc = 0; cc < NC / 2; ++cc) {
+                    for (int cc = 0; cc < NW; ++cc) {
                         const uint2 q = p2[cc];
-                        v[2 * cc][d] = q.x; v[2 * cc + 1][d] = q.y;
+                        w[2 * cc] = q.x; w[2 * cc + 1] = q.y;
                     }
+#pragma unroll
+                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[SKIP + cc];
                 }
             } else {
 #pragma unroll
