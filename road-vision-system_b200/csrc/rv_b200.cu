@@ -85,6 +85,23 @@ void build_ycc_table(YccTabs &y)
     }
 }
 
+// Histogram-pass LAB luminance tables (layout: rv_kernels.cuh, LabHistTabs), from the same gamma and cube-root tables.
+void build_lab_hist_table(LabHistTabs &t)
+{
+    memset(&t, 0, sizeof t);
+    for (int v = 0; v < 256; ++v) {
+        t.pm[0][v] = 871u * RV_LAB_G8[v];
+        t.pm[1][v] = 2929u * RV_LAB_G8[v];
+        t.pm[2][v] = 296u * RV_LAB_G8[v] + 2048u;
+    }
+    const int ncb = (int)(sizeof RV_LAB_CB / sizeof RV_LAB_CB[0]);
+    for (int i = 0; i < 2048; ++i) {
+        const int fy = i < ncb ? RV_LAB_CB[i] : RV_LAB_CB[ncb - 1];      // indices past the table are unreachable
+        const int L = (296 * fy - 1336934 + 16384) >> 15;
+        t.lq[i] = (uint8_t)(L < 0 ? 0 : (L > 255 ? 255 : L));
+    }
+}
+
 int fail(rv_ctx *c, int code, const char *fmt, ...)
 {
     if (c) {
@@ -693,6 +710,11 @@ int rv_create(int device, rv_ctx **out)
     cudaError_t e = cudaMemcpyToSymbol(g_lab, t, sizeof *t);
     delete t;
     if (e != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
+    {
+        LabHistTabs lh;
+        build_lab_hist_table(lh);
+        if (cudaMemcpyToSymbol(g_labh, &lh, sizeof lh) != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
+    }
     {
         YccTabs y;
         build_ycc_table(y);

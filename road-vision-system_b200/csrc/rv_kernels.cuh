@@ -136,13 +136,21 @@ __device__ __forceinline__ void ycrcb_inv(int Y, int Cr, int Cb, int &B, int &G,
 // A.5
 __device__ __forceinline__ int gray_of(int B, int G, int R) { return (3735 * B + 19235 * G + 9798 * R + 16384) >> 15; }
 
-// A.2 forward, luminance only
-__device__ __forceinline__ int lab_L(const LabTabs *t, int B, int G, int R)
+// A.2 forward, luminance only, for the histogram pass: the three gamma look-ups and the Y row of the matrix folded into
+// pre-multiplied tables (pm[0][R] = 871 g8[R], pm[1][G] = 2929 g8[G], pm[2][B] = 296 g8[B] + 2048) and the cube-root
+// look-up folded with the L formula (lq[i] = (296 cb[i] - 1336934 + 16384) >> 15).  Same integers as lab_fwd's L; built on the
+// host (rv_b200.cu: build_lab_hist_table) and checked over all 2^24 colours by the luminance-plane test.
+struct LabHistTabs {
+    uint32_t pm[3][256];
+    uint8_t lq[2048];
+};
+static_assert(sizeof(LabHistTabs) % 16 == 0, "LabHistTabs must be 16-byte granular");
+__device__ LabHistTabs g_labh;
+__device__ __forceinline__ int lab_L_fast(const LabHistTabs *t, int B, int G, int R)
 {
-    const int r = t->g8[R], g = t->g8[G], b = t->g8[B];
-    const int fY = t->cb[(871 * r + 2929 * g + 296 * b + 2048) >> 12];
-    return (296 * fY - 1336934 + 16384) >> 15;
+    return t->lq[(t->pm[0][R] + t->pm[1][G] + t->pm[2][B]) >> 12];
 }
+
 // A.2 forward, all three
 __device__ __forceinline__ void lab_fwd(const LabTabs *t, int B, int G, int R, int &L, int &a, int &bb)
 {
@@ -218,14 +226,18 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
     uint8_t *const luma = EXTRA ? luma_arg : nullptr;
     int32_t *const gray_minmax = EXTRA ? gray_arg : nullptr;
     __shared__ uint32_t wh[HIST_WARPS][256];
-    __shared__ __align__(16) unsigned char tab_raw[SPACE == 1 ? sizeof(LabTabs) : 16];
-    LabTabs *tabs = reinterpret_cast<LabTabs *>(tab_raw);
+    __shared__ __align__(16) unsigned char tab_raw[SPACE == 1 ? sizeof(LabHistTabs) : 16];
+    LabHistTabs *tabs = reinterpret_cast<LabHistTabs *>(tab_raw);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int tile = blockIdx.y, f = blockIdx.z;
     const int ty = tile / g.grid, tx = tile - ty * g.grid;
     for (int i = tid; i < HIST_WARPS * 256; i += HIST_THREADS) (&wh[0][0])[i] = 0;
-    if (SPACE == 1) copy_lab_tabs(tabs);
+    if (SPACE == 1) {
+        const uint4 *ts = reinterpret_cast<const uint4 *>(&g_labh);
+        uint4 *td = reinterpret_cast<uint4 *>(tabs);
+        for (int i = tid; i < (int)(sizeof(LabHistTabs) / 16); i += HIST_THREADS) td[i] = __ldg(ts + i);
+    }
     __syncthreads();
 
     const uint8_t *frame = src + (size_t)f * fstride;
@@ -238,7 +250,7 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
 
     auto one = [&](int B, int G, int R) -> int {
         int v;
-        if (SPACE == 1) v = lab_L(tabs, B, G, R);
+        if (SPACE == 1) v = lab_L_fast(tabs, B, G, R);
         else v = (4899 * R + 9617 * G + 1868 * B + 8192) >> 14;
         atomicAdd(&myh[v], 1u);
         return v;
