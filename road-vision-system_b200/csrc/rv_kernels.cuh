@@ -64,12 +64,14 @@ __device__ __forceinline__ void rv_ce_fma(uint32_t a, uint32_t b, uint32_t &lo, 
     if constexpr (((n) % (den)) < (num)) rv_ce_fma(a, b, lo, hi);  \
     else { lo = __vminu2(a, b); hi = __vmaxu2(a, b); }
 #define RV_CEX(n, lo, hi, a, b) RV_CEX_MIX(RV_FMA_NUM, RV_FMA_DEN, n, lo, hi, a, b)
-// the 3x3 network has few full compare-exchanges (26 of 80 ops); its kernel is ALU-heavier, so more of them go to the FMA pipe
+// the 3x3 networks have few full compare-exchanges (64 of 212 ops in the two-row one) and their kernel's CLAHE phase is
+// ALU-heavy, so more of them go to the FMA pipe: 2/3 measured best (1/2: -1.1 %, 3/5: -0.5 %, 1/1: -4.6 %)
 #ifndef RV_FMA3_NUM
-#define RV_FMA3_NUM 1
-#define RV_FMA3_DEN 2
+#define RV_FMA3_NUM 2
+#define RV_FMA3_DEN 3
 #endif
 #define RV_CEX3(n, lo, hi, a, b) RV_CEX_MIX(RV_FMA3_NUM, RV_FMA3_DEN, n, lo, hi, a, b)
+#define RV_CEX3X2 RV_CEX3              // the production 3x3 network (two rows per task) takes the k3 mix
 
 #ifndef RV_MEDIAN_NET_FILE
 #define RV_MEDIAN_NET_FILE "rv_median_net.h"      // tools/exp_median_order.py builds the kernel against alternative emissions
