@@ -327,10 +327,12 @@ int launch_lut(rv_ctx *ctx, const int32_t *hist, const Geo &g, double clip_limit
 {
     const int clip = clip_int(clip_limit, g);
     const float lut_scale = 255.0f / (float)(g.tw * g.th);
-    dim3 grid((g.grid + 1) * (g.grid + 1), n);
     {
         ScopedTiming tm(ctx, st, 1);
-        k_build_lut<<<grid, 128, 0, st>>>(hist, g.grid, clip, lut_scale, lut, quads);
+        if (g.grid <= LUT_ROWS_MAX_GRID)
+            k_build_lut_rows<<<dim3(g.grid + 1, n), 64 * g.grid, 0, st>>>(hist, g.grid, clip, lut_scale, lut, quads);
+        else
+            k_build_lut<<<dim3((g.grid + 1) * (g.grid + 1), n), 128, 0, st>>>(hist, g.grid, clip, lut_scale, lut, quads);
     }
     ctx->launches++;
     CK(cudaGetLastError());

@@ -402,22 +402,13 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
 // quad q=(qy,qx): tiles ty in {max(qy-1,0), min(qy,grid-1)}, tx likewise (A.3 tx1/tx2 clamping).
 // quads[f][q][v] = lut[ty1][tx1][v] | lut[ty1][tx2][v]<<8 | lut[ty2][tx1][v]<<16 | lut[ty2][tx2][v]<<24
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_build_lut(const int32_t *__restrict__ hist, int grid, int clip, float lut_scale,
-            uint8_t *__restrict__ lut, uint32_t *__restrict__ quads)
+// one warp: the 256-entry LUT of one tile from its histogram (clip, redistribute, prefix sum, scale; A.3), 8 bins per lane,
+// returned as eight packed bytes (lo = bins 8*lane .. +3, hi = +4 .. +7)
+__device__ __forceinline__ uint2 tile_lut_warp(const int32_t *__restrict__ hist_tile, int clip, float lut_scale, int lane)
 {
-    __shared__ __align__(16) uint8_t sl[4][256];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int q = blockIdx.x, f = blockIdx.y;
-    const int nq1 = grid + 1;
-    const int qy = q / nq1, qx = q - qy * nq1;
-    const int ty = (w >> 1) ? min(qy, grid - 1) : max(qy - 1, 0);
-    const int tx = (w & 1) ? min(qx, grid - 1) : max(qx - 1, 0);
-    const size_t tile = (size_t)f * grid * grid + ty * grid + tx;
-
     int h[8];
     {
-        const int4 *hp = reinterpret_cast<const int4 *>(hist + tile * 256 + lane * 8);
+        const int4 *hp = reinterpret_cast<const int4 *>(hist_tile + lane * 8);
         const int4 a = __ldg(hp), b = __ldg(hp + 1);
         h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
     }
@@ -452,13 +443,58 @@ k_build_lut(const int32_t *__restrict__ hist, int grid, int clip, float lut_scal
         const uint32_t u = (uint32_t)sat8(__float2int_rn(v));
         if (i < 4) lo |= u << (8 * i); else hi |= u << (8 * (i - 4));
     }
-    *reinterpret_cast<uint2 *>(&sl[w][lane * 8]) = make_uint2(lo, hi);
+    return make_uint2(lo, hi);
+}
+
+__global__ void __launch_bounds__(128)
+k_build_lut(const int32_t *__restrict__ hist, int grid, int clip, float lut_scale,
+            uint8_t *__restrict__ lut, uint32_t *__restrict__ quads)
+{
+    __shared__ __align__(16) uint8_t sl[4][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int q = blockIdx.x, f = blockIdx.y;
+    const int nq1 = grid + 1;
+    const int qy = q / nq1, qx = q - qy * nq1;
+    const int ty = (w >> 1) ? min(qy, grid - 1) : max(qy - 1, 0);
+    const int tx = (w & 1) ? min(qx, grid - 1) : max(qx - 1, 0);
+    const size_t tile = (size_t)f * grid * grid + ty * grid + tx;
+    const uint2 l8 = tile_lut_warp(hist + tile * 256, clip, lut_scale, lane);
+    *reinterpret_cast<uint2 *>(&sl[w][lane * 8]) = l8;
     if (lut != nullptr && w == 3 && qy < grid && qx < grid)      // warp 3 of quad (ty,tx) owns tile (ty,tx)
-        *reinterpret_cast<uint2 *>(lut + tile * 256 + lane * 8) = make_uint2(lo, hi);
+        *reinterpret_cast<uint2 *>(lut + tile * 256 + lane * 8) = l8;
     __syncthreads();
     uint32_t *qo = quads + ((size_t)f * nq1 * nq1 + q) * 256;
     for (int v = threadIdx.x; v < 256; v += 128)
         qo[v] = (uint32_t)sl[0][v] | ((uint32_t)sl[1][v] << 8) | ((uint32_t)sl[2][v] << 16) | ((uint32_t)sl[3][v] << 24);
+}
+
+// Same result, one CTA per (row of quads, frame) for grids up to 16: warp w = (r, tx) builds the LUT of tile
+// (r ? min(qy, grid-1) : max(qy-1, 0), tx) once for all grid+1 quads of the row -- every tile LUT is built twice per frame
+// instead of four times and the whole pass is a single wave of CTAs.  block = 64 * grid threads.
+constexpr int LUT_ROWS_MAX_GRID = 16;
+__global__ void __launch_bounds__(64 * LUT_ROWS_MAX_GRID)
+k_build_lut_rows(const int32_t *__restrict__ hist, int grid, int clip, float lut_scale,
+                 uint8_t *__restrict__ lut, uint32_t *__restrict__ quads)
+{
+    __shared__ __align__(16) uint8_t sl[2 * LUT_ROWS_MAX_GRID][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int qy = blockIdx.x, f = blockIdx.y;
+    const int nq1 = grid + 1;
+    const int r = w >= grid ? 1 : 0, tx = w - r * grid;
+    const int ty = r ? min(qy, grid - 1) : max(qy - 1, 0);
+    const size_t tile = (size_t)f * grid * grid + ty * grid + tx;
+    const uint2 l8 = tile_lut_warp(hist + tile * 256, clip, lut_scale, lane);
+    *reinterpret_cast<uint2 *>(&sl[w][lane * 8]) = l8;
+    if (lut != nullptr && r == 1 && qy < grid)                   // the lower tile row of quad row qy = tile row qy: written once
+        *reinterpret_cast<uint2 *>(lut + tile * 256 + lane * 8) = l8;
+    __syncthreads();
+    uint32_t *qo = quads + ((size_t)f * nq1 * nq1 + (size_t)qy * nq1) * 256;
+    for (int i = threadIdx.x; i < nq1 * 256; i += blockDim.x) {
+        const int qx = i >> 8, v = i & 255;
+        const int t1 = max(qx - 1, 0), t2 = min(qx, grid - 1);
+        qo[i] = (uint32_t)sl[t1][v] | ((uint32_t)sl[t2][v] << 8) | ((uint32_t)sl[grid + t1][v] << 16) |
+                ((uint32_t)sl[grid + t2][v] << 24);
+    }
 }
 
 // per frame: flag = (max - min < thresh)  (pipeline.py:24-30)
