@@ -69,7 +69,7 @@ const char *rv_version(void);
 int rv_device_count(void);
 
 /* Host-only (no GPU needed): copies the 1024-word YCrCb chroma round-trip table that rv_create uploads for k_chain into
- * out1024 (layout: csrc/rv_kernels.cuh, YccTabs).  It replaces, per pixel, the Cr/Cb arithmetic of cv2.cvtColor
+ * out1024 (layout: csrc/rv_colour.cuh, YccTabs).  It replaces, per pixel, the Cr/Cb arithmetic of cv2.cvtColor
  * (COLOR_BGR2YCrCb / COLOR_YCrCb2BGR; reference: src/preprocess/ops/clahe_dehaze.py:27-30); exposed so that the CPU test
  * suite can check it exhaustively against the oracle.  Returns RV_OK. */
 int rv_ycc_table(uint32_t *out1024);

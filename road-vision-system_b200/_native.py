@@ -39,7 +39,7 @@ def library_path():
 
 def build_library(force=False, verbose=False):
     """Compile csrc/ for sm_100a with nvcc (works without a GPU)."""
-    srcs = [os.path.join(_CSRC, f) for f in ("rv_b200.cu", "rv_kernels.cuh", "rv_lab_tables.h", "rv_median_net.h")]
+    srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith((".cu", ".cuh", ".h")) or f == "Makefile"]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "rv_b200.h"))
     srcs = [s for s in srcs if os.path.exists(s)]
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)

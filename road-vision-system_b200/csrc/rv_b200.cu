@@ -1,5 +1,5 @@
 /*
- * rv_b200.cu -- C ABI (include/rv_b200.h) over the sm_100a kernels in rv_kernels.cuh.
+ * rv_b200.cu -- C ABI (include/rv_b200.h) over the sm_100a kernels in rv_kernels.cuh (rv_common / rv_colour / rv_hist_lut / rv_chain).
  *
  * Host-side logic of the drop-in boundary: parameter validation, CLAHE geometry
  * (clahe.cpp semantics), workspaces, the hist -> lut -> apply+median launch
@@ -68,7 +68,7 @@ struct rv_ctx {
 
 namespace {
 
-// Chroma round-trip tables of k_chain (layout: rv_kernels.cuh, YccTabs).  Same integer formulas as A.1.
+// Chroma round-trip tables of k_chain (layout: rv_colour.cuh, YccTabs).  Same integer formulas as A.1.
 void build_ycc_table(YccTabs &y)
 {
     memset(&y, 0, sizeof y);
@@ -85,7 +85,7 @@ void build_ycc_table(YccTabs &y)
     }
 }
 
-// Histogram-pass LAB luminance tables (layout: rv_kernels.cuh, LabHistTabs), from the same gamma and cube-root tables.
+// Histogram-pass LAB luminance tables (layout: rv_colour.cuh, LabHistTabs), from the same gamma and cube-root tables.
 void build_lab_hist_table(LabHistTabs &t)
 {
     memset(&t, 0, sizeof t);

@@ -1,0 +1,130 @@
+/*
+ * rv_colour.cuh -- OpenCV's 8-bit fixed-point colour arithmetic and the device tables
+ * that carry it: LAB gamma / cube-root / inverse tables, the YCrCb chroma round-trip table of k_chain, the folded LAB
+ * luminance tables of the histogram pass.  The reference only calls cv2.cvtColor: src/preprocess/ops/clahe_dehaze.py:22-30.
+ */
+#pragma once
+#include "rv_common.cuh"
+#include "rv_lab_tables.h"
+
+namespace rv {
+
+
+// ---------------------------------------------------------------------------------------------
+// LAB tables in global memory (copied into shared memory by the kernels that need them)
+// ---------------------------------------------------------------------------------------------
+struct LabTabs {
+    uint16_t g8[256];
+    uint16_t yt[256];
+    uint16_t ft[256];
+    uint16_t cb[2048];     // entries 0..2040 reachable; [2041..2047] padding
+    uint8_t ig[4096];
+};
+static_assert(sizeof(LabTabs) % 16 == 0, "LabTabs must be 16-byte granular");
+__device__ LabTabs g_lab;   // filled once per context from rv_lab_tables.h
+
+// YCrCb chroma round trip (A.1) as two 511-entry tables indexed by d + 255, d = B - Y (first 512 words) or R - Y (next 512).
+// Cb and Cr only pass through the CLAHE, so B' = Y' + fB(d_B), R' = Y' + fR(d_R) and G' = Y' + ((tB + tR + 8192) >> 14) with
+//   fB = ((Cb - 128) * 29049 + 8192) >> 14,  tB = (Cb - 128) * -5636   (Cb = sat8((d * 9241 + (128 << 14) + 8192) >> 14)),
+//   fR = ((Cr - 128) * 22987 + 8192) >> 14,  tR = (Cr - 128) * -11698  (Cr likewise with 11682);  tB, tR and 8192 are even.
+// Entry: bits 22..31 = f + 256, bits 0..21 = t / 2 modulo 2^22 (+ 4096 + 2^21 in the R table, so that the sum of the two
+// fields lies in [0, 2^22)): ((eB + eR) << 10) >> 23 == 256 + ((tB + tR + 8192) >> 14), e >> 22 == f + 256 -- a shift-and-add
+// (LEA.HI) per channel.  Built on the host (rv_b200.cu: build_ycc_table) with the same integer formulas.
+struct YccTabs { uint32_t e[1024]; };
+__device__ YccTabs g_ycc;
+
+
+// A.1 luminance straight from the packed pixel word (B, G, R, x): Y = (1868 B + 9617 G + 4899 R + 8192) >> 14 as two
+// chained 16-bit x 8-bit dot products (IDP.2A.LO takes bytes 0,1, IDP.2A.HI bytes 2,3; the x byte meets a zero coefficient)
+__device__ __forceinline__ uint32_t luma_y(uint32_t px)
+{
+    constexpr uint32_t CBG = 1868u | (9617u << 16), CR0 = 4899u;
+    return __dp2a_hi(CR0, px, __dp2a_lo(CBG, px, 8192u)) >> 14;
+}
+
+// A.1 forward
+__device__ __forceinline__ void ycrcb_fwd(int B, int G, int R, int &Y, int &Cr, int &Cb)
+{
+    Y = (4899 * R + 9617 * G + 1868 * B + 8192) >> 14;
+    Cr = sat8(((R - Y) * 11682 + ((128 << 14) + 8192)) >> 14);
+    Cb = sat8(((B - Y) * 9241 + ((128 << 14) + 8192)) >> 14);
+}
+// A.1 inverse
+__device__ __forceinline__ void ycrcb_inv(int Y, int Cr, int Cb, int &B, int &G, int &R)
+{
+    const int cb = Cb - 128, cr = Cr - 128;
+    B = sat8(Y + ((cb * 29049 + 8192) >> 14));
+    G = sat8(Y + ((cb * -5636 + cr * -11698 + 8192) >> 14));
+    R = sat8(Y + ((cr * 22987 + 8192) >> 14));
+}
+// A.5
+__device__ __forceinline__ int gray_of(int B, int G, int R) { return (3735 * B + 19235 * G + 9798 * R + 16384) >> 15; }
+
+// A.2 forward, luminance only, for the histogram pass: the three gamma look-ups and the Y row of the matrix folded into
+// pre-multiplied tables (pm[0][R] = 871 g8[R], pm[1][G] = 2929 g8[G], pm[2][B] = 296 g8[B] + 2048) and the cube-root
+// look-up folded with the L formula (lq[i] = (296 cb[i] - 1336934 + 16384) >> 15).  Same integers as lab_fwd's L; built on the
+// host (rv_b200.cu: build_lab_hist_table) and checked over all 2^24 colours by the luminance-plane test.
+struct LabHistTabs {
+    uint32_t pm[3][256];
+    uint8_t lq[2048];
+};
+static_assert(sizeof(LabHistTabs) % 16 == 0, "LabHistTabs must be 16-byte granular");
+__device__ LabHistTabs g_labh;
+__device__ __forceinline__ int lab_L_fast(const LabHistTabs *t, int B, int G, int R)
+{
+    return t->lq[(t->pm[0][R] + t->pm[1][G] + t->pm[2][B]) >> 12];
+}
+
+// A.2 forward, all three
+__device__ __forceinline__ void lab_fwd(const LabTabs *t, int B, int G, int R, int &L, int &a, int &bb)
+{
+    const int r = t->g8[R], g = t->g8[G], b = t->g8[B];
+    const int fX = t->cb[(1777 * r + 1541 * g + 778 * b + 2048) >> 12];
+    const int fY = t->cb[(871 * r + 2929 * g + 296 * b + 2048) >> 12];
+    const int fZ = t->cb[(73 * r + 448 * g + 3575 * b + 2048) >> 12];
+    // over all 2^24 colours a stays in [42,226] and b in [20,223] (tests/test_oracle.py::test_lab_forward_ranges): no saturation needed
+    L = (296 * fY - 1336934 + 16384) >> 15;
+    a = (500 * (fX - fY) + ((128 << 15) + 16384)) >> 15;
+    bb = (200 * (fY - fZ) + ((128 << 15) + 16384)) >> 15;
+}
+__device__ __forceinline__ int lab_xz(int i)
+{
+    const int lin = (i * 108) / 841 - 290;            // truncating division, as in C
+    const int cub = (((i * i) >> 14) * i) >> 14;
+    return i <= 3390 ? lin : cub;
+}
+// A.2 inverse.  lab_inv_args gives the two XZ arguments; when every argument in the warp is above 3390 (any pixel that is not
+// nearly black) the caller uses CUBIC_ONLY = true and the linear branch of XZ with its division is never evaluated.
+__device__ __forceinline__ void lab_inv_args(const LabTabs *t, int L, int a, int b, int &y, int &ix, int &iz)
+{
+    y = t->yt[L];
+    const int fy = t->ft[L];
+    const int adiv = ((5 * a * 53687 + 128) >> 13) - 4194;
+    const int bdiv = ((b * 41943 + 16) >> 9) - 10485 + 1;
+    ix = fy + adiv;
+    iz = fy - bdiv;
+}
+template <bool CUBIC_ONLY>
+__device__ __forceinline__ void lab_inv_tail(const LabTabs *t, int y, int ix, int iz, int &B, int &G, int &R)
+{
+    const int x = CUBIC_ONLY ? ((((ix * ix) >> 14) * ix) >> 14) : lab_xz(ix);
+    const int z = CUBIC_ONLY ? ((((iz * iz) >> 14) * iz) >> 14) : lab_xz(iz);
+    int ro = (12615 * x - 6296 * y - 2223 * z + 8192) >> 14;
+    int go = (-3773 * x + 7684 * y + 185 * z + 8192) >> 14;
+    int bo = (217 * x - 836 * y + 4715 * z + 8192) >> 14;
+    ro = min(max(ro, 0), 4095);
+    go = min(max(go, 0), 4095);
+    bo = min(max(bo, 0), 4095);
+    B = t->ig[bo];
+    G = t->ig[go];
+    R = t->ig[ro];
+}
+
+__device__ __forceinline__ void copy_lab_tabs(LabTabs *dst)
+{
+    const uint4 *s = reinterpret_cast<const uint4 *>(&g_lab);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(LabTabs) / 16); i += blockDim.x) d[i] = s[i];
+}
+
+}  // namespace rv

@@ -1,5 +1,7 @@
 /*
- * rv_kernels.cuh -- sm_100a kernels of the preprocessing chain (CLAHEDehaze -> MedianDerain).
+ * rv_kernels.cuh -- sm_100a kernels of the preprocessing chain (CLAHEDehaze -> MedianDerain); umbrella over
+ * rv_common.cuh (geometry, TMA helpers), rv_colour.cuh (colour arithmetic + tables), rv_hist_lut.cuh (k_luma_hist,
+ * k_build_lut*), rv_chain.cuh (k_chain, k_letterbox).
  *
  * Arithmetic follows OpenCV's 8-bit fixed-point paths exactly; the
  * reference only *calls* them: /root/reference/src/preprocess/ops/clahe_dehaze.py:19-30 and
@@ -18,1176 +20,7 @@
  *   k_letterbox   detector-input stage, general form (cv2.resize INTER_LINEAR arithmetic, RGB fp16 NCHW)
  */
 #pragma once
-#include <cuda.h>
-#include <cuda_runtime.h>
-#include <stdint.h>
-
-#include <cuda_fp16.h>
-
-#include <type_traits>
-
-#include "rv_lab_tables.h"
-
-// Median compare-exchange forms.  Plane values are kept as 0x6400|v per 16-bit lane: as unsigned
-// integers they order like v (VIMNMX.U16x2, ALU pipe) and as IEEE halves they are 1024+v, exactly
-// representable together with every difference and sum used below (HFMA2/HADD2, FMA pipe).  On sm_100a both
-// pipes issue 64 lanes/clk/SM (tools/ubench_minmax.cu), so a fraction RV_FMA_NUM/RV_FMA_DEN of the
-// compare-exchanges runs on the FMA pipe:  s = relu(b - a);  max = a + s;  min = b - s.
-#ifndef RV_FMA_NUM
-#define RV_FMA_NUM 0
-#endif
-#ifndef RV_FMA_DEN
-#define RV_FMA_DEN 1
-#endif
-#define RV_PLANE_BIAS 0x64006400u
-#ifndef RV_HIST_DP4A
-#define RV_HIST_DP4A 1
-#endif
-#ifndef RV_MEDIAN5_2ROW
-#define RV_MEDIAN5_2ROW 1
-#endif
-#ifndef RV_MEDIAN3_2ROW
-#define RV_MEDIAN3_2ROW 1
-#endif
-__device__ __forceinline__ void rv_ce_fma(uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi)
-{
-    const __half2 x = *reinterpret_cast<const __half2 *>(&a), y = *reinterpret_cast<const __half2 *>(&b);
-    const uint32_t m1bits = 0xBC00BC00u;                       // (-1, -1)
-    const __half2 m1 = *reinterpret_cast<const __half2 *>(&m1bits);
-    const __half2 s = __hfma2_relu(x, m1, y);                  // relu(y - x)
-    const __half2 h = __hadd2(x, s), l = __hsub2(y, s);
-    hi = *reinterpret_cast<const uint32_t *>(&h);
-    lo = *reinterpret_cast<const uint32_t *>(&l);
-}
-#define RV_CEX_MIX(num, den, n, lo, hi, a, b)                      \
-    uint32_t lo, hi;                                               \
-    if constexpr (((n) % (den)) < (num)) rv_ce_fma(a, b, lo, hi);  \
-    else { lo = __vminu2(a, b); hi = __vmaxu2(a, b); }
-#define RV_CEX(n, lo, hi, a, b) RV_CEX_MIX(RV_FMA_NUM, RV_FMA_DEN, n, lo, hi, a, b)
-// the 3x3 networks have few full compare-exchanges (64 of 212 ops in the two-row one) and their kernel's CLAHE phase is
-// ALU-heavy, so more of them go to the FMA pipe: 2/3 measured best (1/2: -1.1 %, 3/5: -0.5 %, 1/1: -4.6 %)
-#ifndef RV_FMA3_NUM
-#define RV_FMA3_NUM 2
-#define RV_FMA3_DEN 3
-#endif
-#define RV_CEX3(n, lo, hi, a, b) RV_CEX_MIX(RV_FMA3_NUM, RV_FMA3_DEN, n, lo, hi, a, b)
-#define RV_CEX3X2 RV_CEX3              // the production 3x3 network (two rows per task) takes the k3 mix
-
-#ifndef RV_MEDIAN_NET_FILE
-#define RV_MEDIAN_NET_FILE "rv_median_net.h"      // tools/exp_median_order.py builds the kernel against alternative emissions
-#endif
-#include RV_MEDIAN_NET_FILE
-
-namespace rv {
-
-struct Geo {
-    int H, W;          // frame size
-    int grid;          // tiles per side
-    int tw, th;        // tile size of the (REFLECT_101-padded) plane, clahe.cpp semantics (A.3)
-    float inv_tw, inv_th;
-};
-
-// ---------------------------------------------------------------------------------------------
-// LAB tables in global memory (copied into shared memory by the kernels that need them)
-// ---------------------------------------------------------------------------------------------
-struct LabTabs {
-    uint16_t g8[256];
-    uint16_t yt[256];
-    uint16_t ft[256];
-    uint16_t cb[2048];     // entries 0..2040 reachable; [2041..2047] padding
-    uint8_t ig[4096];
-};
-static_assert(sizeof(LabTabs) % 16 == 0, "LabTabs must be 16-byte granular");
-__device__ LabTabs g_lab;   // filled once per context from rv_lab_tables.h
-
-// YCrCb chroma round trip (A.1) as two 511-entry tables indexed by d + 255, d = B - Y (first 512 words) or R - Y (next 512).
-// Cb and Cr only pass through the CLAHE, so B' = Y' + fB(d_B), R' = Y' + fR(d_R) and G' = Y' + ((tB + tR + 8192) >> 14) with
-//   fB = ((Cb - 128) * 29049 + 8192) >> 14,  tB = (Cb - 128) * -5636   (Cb = sat8((d * 9241 + (128 << 14) + 8192) >> 14)),
-//   fR = ((Cr - 128) * 22987 + 8192) >> 14,  tR = (Cr - 128) * -11698  (Cr likewise with 11682);  tB, tR and 8192 are even.
-// Entry: bits 22..31 = f + 256, bits 0..21 = t / 2 modulo 2^22 (+ 4096 + 2^21 in the R table, so that the sum of the two
-// fields lies in [0, 2^22)): ((eB + eR) << 10) >> 23 == 256 + ((tB + tR + 8192) >> 14), e >> 22 == f + 256 -- a shift-and-add
-// (LEA.HI) per channel.  Built on the host (rv_b200.cu: build_ycc_table) with the same integer formulas.
-struct YccTabs { uint32_t e[1024]; };
-__device__ YccTabs g_ycc;
-
-__device__ __forceinline__ int sat8(int v) { return min(max(v, 0), 255); }
-
-// A.1 luminance straight from the packed pixel word (B, G, R, x): Y = (1868 B + 9617 G + 4899 R + 8192) >> 14 as two
-// chained 16-bit x 8-bit dot products (IDP.2A.LO takes bytes 0,1, IDP.2A.HI bytes 2,3; the x byte meets a zero coefficient)
-__device__ __forceinline__ uint32_t luma_y(uint32_t px)
-{
-    constexpr uint32_t CBG = 1868u | (9617u << 16), CR0 = 4899u;
-    return __dp2a_hi(CR0, px, __dp2a_lo(CBG, px, 8192u)) >> 14;
-}
-
-// A.1 forward
-__device__ __forceinline__ void ycrcb_fwd(int B, int G, int R, int &Y, int &Cr, int &Cb)
-{
-    Y = (4899 * R + 9617 * G + 1868 * B + 8192) >> 14;
-    Cr = sat8(((R - Y) * 11682 + ((128 << 14) + 8192)) >> 14);
-    Cb = sat8(((B - Y) * 9241 + ((128 << 14) + 8192)) >> 14);
-}
-// A.1 inverse
-__device__ __forceinline__ void ycrcb_inv(int Y, int Cr, int Cb, int &B, int &G, int &R)
-{
-    const int cb = Cb - 128, cr = Cr - 128;
-    B = sat8(Y + ((cb * 29049 + 8192) >> 14));
-    G = sat8(Y + ((cb * -5636 + cr * -11698 + 8192) >> 14));
-    R = sat8(Y + ((cr * 22987 + 8192) >> 14));
-}
-// A.5
-__device__ __forceinline__ int gray_of(int B, int G, int R) { return (3735 * B + 19235 * G + 9798 * R + 16384) >> 15; }
-
-// A.2 forward, luminance only, for the histogram pass: the three gamma look-ups and the Y row of the matrix folded into
-// pre-multiplied tables (pm[0][R] = 871 g8[R], pm[1][G] = 2929 g8[G], pm[2][B] = 296 g8[B] + 2048) and the cube-root
-// look-up folded with the L formula (lq[i] = (296 cb[i] - 1336934 + 16384) >> 15).  Same integers as lab_fwd's L; built on the
-// host (rv_b200.cu: build_lab_hist_table) and checked over all 2^24 colours by the luminance-plane test.
-struct LabHistTabs {
-    uint32_t pm[3][256];
-    uint8_t lq[2048];
-};
-static_assert(sizeof(LabHistTabs) % 16 == 0, "LabHistTabs must be 16-byte granular");
-__device__ LabHistTabs g_labh;
-__device__ __forceinline__ int lab_L_fast(const LabHistTabs *t, int B, int G, int R)
-{
-    return t->lq[(t->pm[0][R] + t->pm[1][G] + t->pm[2][B]) >> 12];
-}
-
-// A.2 forward, all three
-__device__ __forceinline__ void lab_fwd(const LabTabs *t, int B, int G, int R, int &L, int &a, int &bb)
-{
-    const int r = t->g8[R], g = t->g8[G], b = t->g8[B];
-    const int fX = t->cb[(1777 * r + 1541 * g + 778 * b + 2048) >> 12];
-    const int fY = t->cb[(871 * r + 2929 * g + 296 * b + 2048) >> 12];
-    const int fZ = t->cb[(73 * r + 448 * g + 3575 * b + 2048) >> 12];
-    // over all 2^24 colours a stays in [42,226] and b in [20,223] (tests/test_oracle.py::test_lab_forward_ranges): no saturation needed
-    L = (296 * fY - 1336934 + 16384) >> 15;
-    a = (500 * (fX - fY) + ((128 << 15) + 16384)) >> 15;
-    bb = (200 * (fY - fZ) + ((128 << 15) + 16384)) >> 15;
-}
-__device__ __forceinline__ int lab_xz(int i)
-{
-    const int lin = (i * 108) / 841 - 290;            // truncating division, as in C
-    const int cub = (((i * i) >> 14) * i) >> 14;
-    return i <= 3390 ? lin : cub;
-}
-// A.2 inverse.  lab_inv_args gives the two XZ arguments; when every argument in the warp is above 3390 (any pixel that is not
-// nearly black) the caller uses CUBIC_ONLY = true and the linear branch of XZ with its division is never evaluated.
-__device__ __forceinline__ void lab_inv_args(const LabTabs *t, int L, int a, int b, int &y, int &ix, int &iz)
-{
-    y = t->yt[L];
-    const int fy = t->ft[L];
-    const int adiv = ((5 * a * 53687 + 128) >> 13) - 4194;
-    const int bdiv = ((b * 41943 + 16) >> 9) - 10485 + 1;
-    ix = fy + adiv;
-    iz = fy - bdiv;
-}
-template <bool CUBIC_ONLY>
-__device__ __forceinline__ void lab_inv_tail(const LabTabs *t, int y, int ix, int iz, int &B, int &G, int &R)
-{
-    const int x = CUBIC_ONLY ? ((((ix * ix) >> 14) * ix) >> 14) : lab_xz(ix);
-    const int z = CUBIC_ONLY ? ((((iz * iz) >> 14) * iz) >> 14) : lab_xz(iz);
-    int ro = (12615 * x - 6296 * y - 2223 * z + 8192) >> 14;
-    int go = (-3773 * x + 7684 * y + 185 * z + 8192) >> 14;
-    int bo = (217 * x - 836 * y + 4715 * z + 8192) >> 14;
-    ro = min(max(ro, 0), 4095);
-    go = min(max(go, 0), 4095);
-    bo = min(max(bo, 0), 4095);
-    B = t->ig[bo];
-    G = t->ig[go];
-    R = t->ig[ro];
-}
-
-__device__ __forceinline__ int reflect101(int p, int len)
-{
-    if (len == 1) return 0;
-    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
-    return p;
-}
-
-__device__ __forceinline__ void copy_lab_tabs(LabTabs *dst)
-{
-    const uint4 *s = reinterpret_cast<const uint4 *>(&g_lab);
-    uint4 *d = reinterpret_cast<uint4 *>(dst);
-    for (int i = threadIdx.x; i < (int)(sizeof(LabTabs) / 16); i += blockDim.x) d[i] = s[i];
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1: luminance + per-tile histograms
-// grid = (slices, tiles, frames), block = 256.  hist must be zeroed; slices accumulate with atomics.
-// ---------------------------------------------------------------------------------------------
-constexpr int HIST_THREADS = 256;
-constexpr int HIST_WARPS = HIST_THREADS / 32;
-
-// EXTRA = false is the production instantiation (no luma plane, no gray min/max: nothing but the histogram).
-template <int SPACE, bool EXTRA>
-__global__ void __launch_bounds__(HIST_THREADS)
-k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g, int rows_per_slice,
-            int32_t *__restrict__ hist, uint8_t *__restrict__ luma_arg, int32_t *__restrict__ gray_arg)
-{
-    uint8_t *const luma = EXTRA ? luma_arg : nullptr;
-    int32_t *const gray_minmax = EXTRA ? gray_arg : nullptr;
-    __shared__ uint32_t wh[HIST_WARPS][256];
-    __shared__ __align__(16) unsigned char tab_raw[SPACE == 1 ? sizeof(LabHistTabs) : 16];
-    LabHistTabs *tabs = reinterpret_cast<LabHistTabs *>(tab_raw);
-
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int tile = blockIdx.y, f = blockIdx.z;
-    const int ty = tile / g.grid, tx = tile - ty * g.grid;
-    for (int i = tid; i < HIST_WARPS * 256; i += HIST_THREADS) (&wh[0][0])[i] = 0;
-    if (SPACE == 1) {
-        const uint4 *ts = reinterpret_cast<const uint4 *>(&g_labh);
-        uint4 *td = reinterpret_cast<uint4 *>(tabs);
-        for (int i = tid; i < (int)(sizeof(LabHistTabs) / 16); i += HIST_THREADS) td[i] = __ldg(ts + i);
-    }
-    __syncthreads();
-
-    const uint8_t *frame = src + (size_t)f * fstride;
-    const int x0 = tx * g.tw, y0 = ty * g.th + blockIdx.x * rows_per_slice;
-    const int y1 = min(y0 + rows_per_slice, (ty + 1) * g.th);
-    const int nrows = y1 - y0;
-    uint32_t *myh = wh[warp];
-    int gmin = 255, gmax = 0;
-    const bool want_gray = gray_minmax != nullptr;
-
-    auto one = [&](int B, int G, int R) -> int {
-        int v;
-        if (SPACE == 1) v = lab_L_fast(tabs, B, G, R);
-        else v = (4899 * R + 9617 * G + 1868 * B + 8192) >> 14;
-        atomicAdd(&myh[v], 1u);
-        return v;
-    };
-
-    const bool interior = (x0 + g.tw <= g.W) && (y1 <= g.H);
-    const bool vec_ok = interior && (g.tw % 4 == 0) && (pitch % 4 == 0) &&
-                        ((reinterpret_cast<uintptr_t>(frame) & 3) == 0);
-    const bool vec16_ok = vec_ok && SPACE == 0 && !EXTRA && RV_HIST_DP4A && (g.tw % 16 == 0) && (pitch % 16 == 0) &&
-                          ((reinterpret_cast<uintptr_t>(frame) & 15) == 0);
-    if (nrows > 0 && vec16_ok) {
-        // 16 pixels = 48 bytes = three 16-byte loads per group, two groups in flight per thread; Y straight from the packed
-        // words with byte dot products (no unpacking), one shared-memory atomic per pixel
-        const int gpr = g.tw >> 4;
-        const int total = nrows * gpr;
-        const float inv_gpr = 1.0f / (float)gpr;
-        auto load = [&](int idx, uint4 (&w)[3]) {
-            int r = __float2int_rz(__int2float_rn(idx) * inv_gpr);
-            int gx = idx - r * gpr;
-            if (gx < 0) { gx += gpr; --r; }
-            if (gx >= gpr) { gx -= gpr; ++r; }
-            const uint4 *p = reinterpret_cast<const uint4 *>(frame + (size_t)(y0 + r) * pitch + 3 * (x0 + 16 * gx));
-            w[0] = __ldg(p); w[1] = __ldg(p + 1); w[2] = __ldg(p + 2);
-        };
-        auto quad = [&](uint32_t w0, uint32_t w1, uint32_t w2) {
-            const uint32_t pp[4] = {w0, __funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 16), w2 >> 8};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) atomicAdd(&myh[luma_y(pp[j])], 1u);
-        };
-        auto consume = [&](const uint4 (&w)[3]) {
-            quad(w[0].x, w[0].y, w[0].z);
-            quad(w[0].w, w[1].x, w[1].y);
-            quad(w[1].z, w[1].w, w[2].x);
-            quad(w[2].y, w[2].z, w[2].w);
-        };
-        int idx = tid;
-        for (; idx + HIST_THREADS < total; idx += 2 * HIST_THREADS) {
-            uint4 wa[3], wb[3];
-            load(idx, wa);
-            load(idx + HIST_THREADS, wb);
-            consume(wa);
-            consume(wb);
-        }
-        if (idx < total) {
-            uint4 wa[3];
-            load(idx, wa);
-            consume(wa);
-        }
-    } else if (nrows > 0 && vec_ok) {
-        const int gpr = g.tw >> 2;                 // 4-pixel groups per tile row
-        const int total = nrows * gpr;
-        const float inv_gpr = 1.0f / (float)gpr;
-        auto locate = [&](int idx, int &y, int &x) {
-            int r = __float2int_rz(__int2float_rn(idx) * inv_gpr);
-            int gx = idx - r * gpr;
-            if (gx < 0) { gx += gpr; --r; }
-            if (gx >= gpr) { gx -= gpr; ++r; }
-            y = y0 + r; x = x0 + 4 * gx;
-        };
-        auto process = [&](uint32_t w0, uint32_t w1, uint32_t w2, int y, int x) {
-#if RV_HIST_DP4A
-            if (SPACE == 0 && !EXTRA) {
-                // Y straight from the packed BGRx word (luma_y), no per-channel unpacking
-                const uint32_t p0 = w0, p1 = __funnelshift_r(w0, w1, 24), p2 = __funnelshift_r(w1, w2, 16), p3 = w2 >> 8;
-                const uint32_t pp[4] = {p0, p1, p2, p3};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) atomicAdd(&myh[luma_y(pp[j])], 1u);
-                return;
-            }
-#endif
-            const int B0 = w0 & 255, G0 = (w0 >> 8) & 255, R0 = (w0 >> 16) & 255;
-            const int B1 = w0 >> 24, G1 = w1 & 255, R1 = (w1 >> 8) & 255;
-            const int B2 = (w1 >> 16) & 255, G2 = w1 >> 24, R2 = w2 & 255;
-            const int B3 = (w2 >> 8) & 255, G3 = (w2 >> 16) & 255, R3 = w2 >> 24;
-            const int v0 = one(B0, G0, R0), v1 = one(B1, G1, R1), v2 = one(B2, G2, R2), v3 = one(B3, G3, R3);
-            if (luma) {
-                uint8_t *lp = luma + ((size_t)f * g.H + y) * g.W + x;
-                lp[0] = (uint8_t)v0; lp[1] = (uint8_t)v1; lp[2] = (uint8_t)v2; lp[3] = (uint8_t)v3;
-            }
-            if (want_gray) {
-                const int a0 = gray_of(B0, G0, R0), a1 = gray_of(B1, G1, R1), a2 = gray_of(B2, G2, R2), a3 = gray_of(B3, G3, R3);
-                gmin = min(gmin, min(min(a0, a1), min(a2, a3)));
-                gmax = max(gmax, max(max(a0, a1), max(a2, a3)));
-            }
-        };
-        // four 12-byte groups (48 bytes) in flight per thread: the pass is DRAM-latency bound otherwise
-        constexpr int UNR = 4;
-        int idx = tid;
-        for (; idx + (UNR - 1) * HIST_THREADS < total; idx += UNR * HIST_THREADS) {
-            uint32_t w[UNR][3];
-            int yy[UNR], xx[UNR];
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                locate(idx + u * HIST_THREADS, yy[u], xx[u]);
-                const uint32_t *p = reinterpret_cast<const uint32_t *>(frame + (size_t)yy[u] * pitch + 3 * xx[u]);
-                w[u][0] = __ldg(p); w[u][1] = __ldg(p + 1); w[u][2] = __ldg(p + 2);
-            }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) process(w[u][0], w[u][1], w[u][2], yy[u], xx[u]);
-        }
-        for (; idx < total; idx += HIST_THREADS) {
-            int y, x;
-            locate(idx, y, x);
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(frame + (size_t)y * pitch + 3 * x);
-            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
-            process(w0, w1, w2, y, x);
-        }
-    } else if (nrows > 0) {
-        // generic path: ragged tiles (REFLECT_101 padding), odd tile widths, unaligned buffers
-        const int total = nrows * g.tw;
-        for (int idx = tid; idx < total; idx += HIST_THREADS) {
-            const int r = idx / g.tw, cx = idx - r * g.tw;
-            const int ey = y0 + r, ex = x0 + cx;
-            const int y = reflect101(ey, g.H), x = reflect101(ex, g.W);
-            const uint8_t *p = frame + (size_t)y * pitch + 3 * x;
-            const int B = p[0], G = p[1], R = p[2];
-            const int v = one(B, G, R);
-            if (ey < g.H && ex < g.W) {            // each real pixel is visited exactly once un-reflected
-                if (luma) luma[((size_t)f * g.H + y) * g.W + x] = (uint8_t)v;
-                if (want_gray) { const int a = gray_of(B, G, R); gmin = min(gmin, a); gmax = max(gmax, a); }
-            }
-        }
-    }
-    __syncthreads();
-    {
-        uint32_t s = 0;
-#pragma unroll
-        for (int w = 0; w < HIST_WARPS; ++w) s += wh[w][tid];
-        if (s) atomicAdd(&hist[((size_t)f * g.grid * g.grid + tile) * 256 + tid], (int)s);
-    }
-    if (want_gray) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            gmin = min(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
-            gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
-        }
-        if ((tid & 31) == 0 && gmin <= gmax) {
-            atomicMin(&gray_minmax[2 * f], gmin);
-            atomicMax(&gray_minmax[2 * f + 1], gmax);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2: LUT + quad tables.  grid = ((grid+1)^2 quads, frames), block = 128 (4 warps = the 4 tiles
-// of the quad; each warp rebuilds its tile's LUT -- 256 bins, 8 per lane, shuffle scans).
-// quad q=(qy,qx): tiles ty in {max(qy-1,0), min(qy,grid-1)}, tx likewise (A.3 tx1/tx2 clamping).
-// quads[f][q][v] = lut[ty1][tx1][v] | lut[ty1][tx2][v]<<8 | lut[ty2][tx1][v]<<16 | lut[ty2][tx2][v]<<24
-// ---------------------------------------------------------------------------------------------
-// one warp: the 256-entry LUT of one tile from its histogram (clip, redistribute, prefix sum, scale; A.3), 8 bins per lane,
-// returned as eight packed bytes (lo = bins 8*lane .. +3, hi = +4 .. +7)
-__device__ __forceinline__ uint2 tile_lut_warp(const int32_t *__restrict__ hist_tile, int clip, float lut_scale, int lane)
-{
-    int h[8];
-    {
-        const int4 *hp = reinterpret_cast<const int4 *>(hist_tile + lane * 8);
-        const int4 a = __ldg(hp), b = __ldg(hp + 1);
-        h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
-    }
-    if (clip > 0) {
-        int clipped = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { clipped += max(h[i] - clip, 0); h[i] = min(h[i], clip); }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) clipped += __shfl_xor_sync(0xffffffffu, clipped, o);
-        const int batch = clipped >> 8, residual = clipped & 255;
-        const int step = residual ? max(256 / residual, 1) : 1;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int bin = lane * 8 + i;
-            const int qd = bin / step;
-            h[i] += batch + ((residual && bin - qd * step == 0 && qd < residual) ? 1 : 0);
-        }
-    }
-#pragma unroll
-    for (int i = 1; i < 8; ++i) h[i] += h[i - 1];
-    int run = h[7];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, run, o);
-        if (lane >= o) run += t;
-    }
-    const int base = run - h[7];
-    uint32_t lo = 0, hi = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float v = __fmul_rn(__int2float_rn(base + h[i]), lut_scale);
-        const uint32_t u = (uint32_t)sat8(__float2int_rn(v));
-        if (i < 4) lo |= u << (8 * i); else hi |= u << (8 * (i - 4));
-    }
-    return make_uint2(lo, hi);
-}
-
-__global__ void __launch_bounds__(128)
-k_build_lut(const int32_t *__restrict__ hist, int grid, int clip, float lut_scale,
-            uint8_t *__restrict__ lut, uint32_t *__restrict__ quads)
-{
-    __shared__ __align__(16) uint8_t sl[4][256];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int q = blockIdx.x, f = blockIdx.y;
-    const int nq1 = grid + 1;
-    const int qy = q / nq1, qx = q - qy * nq1;
-    const int ty = (w >> 1) ? min(qy, grid - 1) : max(qy - 1, 0);
-    const int tx = (w & 1) ? min(qx, grid - 1) : max(qx - 1, 0);
-    const size_t tile = (size_t)f * grid * grid + ty * grid + tx;
-    const uint2 l8 = tile_lut_warp(hist + tile * 256, clip, lut_scale, lane);
-    *reinterpret_cast<uint2 *>(&sl[w][lane * 8]) = l8;
-    if (lut != nullptr && w == 3 && qy < grid && qx < grid)      // warp 3 of quad (ty,tx) owns tile (ty,tx)
-        *reinterpret_cast<uint2 *>(lut + tile * 256 + lane * 8) = l8;
-    __syncthreads();
-    uint32_t *qo = quads + ((size_t)f * nq1 * nq1 + q) * 256;
-    for (int v = threadIdx.x; v < 256; v += 128)
-        qo[v] = (uint32_t)sl[0][v] | ((uint32_t)sl[1][v] << 8) | ((uint32_t)sl[2][v] << 16) | ((uint32_t)sl[3][v] << 24);
-}
-
-// Same result, one CTA per (row of quads, frame) for grids up to 16: warp w = (r, tx) builds the LUT of tile
-// (r ? min(qy, grid-1) : max(qy-1, 0), tx) once for all grid+1 quads of the row -- every tile LUT is built twice per frame
-// instead of four times and the whole pass is a single wave of CTAs.  block = 64 * grid threads.
-constexpr int LUT_ROWS_MAX_GRID = 16;
-__global__ void __launch_bounds__(64 * LUT_ROWS_MAX_GRID)
-k_build_lut_rows(const int32_t *__restrict__ hist, int grid, int clip, float lut_scale,
-                 uint8_t *__restrict__ lut, uint32_t *__restrict__ quads)
-{
-    __shared__ __align__(16) uint8_t sl[2 * LUT_ROWS_MAX_GRID][256];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int qy = blockIdx.x, f = blockIdx.y;
-    const int nq1 = grid + 1;
-    const int r = w >= grid ? 1 : 0, tx = w - r * grid;
-    const int ty = r ? min(qy, grid - 1) : max(qy - 1, 0);
-    const size_t tile = (size_t)f * grid * grid + ty * grid + tx;
-    const uint2 l8 = tile_lut_warp(hist + tile * 256, clip, lut_scale, lane);
-    *reinterpret_cast<uint2 *>(&sl[w][lane * 8]) = l8;
-    if (lut != nullptr && r == 1 && qy < grid)                   // the lower tile row of quad row qy = tile row qy: written once
-        *reinterpret_cast<uint2 *>(lut + tile * 256 + lane * 8) = l8;
-    __syncthreads();
-    uint32_t *qo = quads + ((size_t)f * nq1 * nq1 + (size_t)qy * nq1) * 256;
-    for (int i = threadIdx.x; i < nq1 * 256; i += blockDim.x) {
-        const int qx = i >> 8, v = i & 255;
-        const int t1 = max(qx - 1, 0), t2 = min(qx, grid - 1);
-        qo[i] = (uint32_t)sl[t1][v] | ((uint32_t)sl[t2][v] << 8) | ((uint32_t)sl[grid + t1][v] << 16) |
-                ((uint32_t)sl[grid + t2][v] << 24);
-    }
-}
-
-// per frame: flag = (max - min < thresh)  (pipeline.py:24-30)
-__global__ void k_gate_flags(const int32_t *__restrict__ gray_minmax, int n, float thresh, int32_t *__restrict__ flags)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flags[i] = ((float)(gray_minmax[2 * i + 1] - gray_minmax[2 * i]) < thresh) ? 1 : 0;
-}
-
-__global__ void k_init_minmax(int32_t *mm, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { mm[2 * i] = 255; mm[2 * i + 1] = 0; }
-}
-
-// frames the gate skipped are passed through unchanged
-__global__ void k_gate_copy(const uint8_t *__restrict__ src, size_t spitch, size_t sfstride,
-                            uint8_t *__restrict__ dst, size_t dpitch, size_t dfstride,
-                            int H, int rowbytes, const int32_t *__restrict__ flags)
-{
-    const int f = blockIdx.z;
-    if (flags[f]) return;
-    for (int y = blockIdx.y; y < H; y += gridDim.y) {
-        const uint8_t *s = src + (size_t)f * sfstride + (size_t)y * spitch;
-        uint8_t *d = dst + (size_t)f * dfstride + (size_t)y * dpitch;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rowbytes; i += gridDim.x * blockDim.x) d[i] = s[i];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// TMA (cp.async.bulk.tensor) + mbarrier helpers for the box staging of k_chain
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    for (int spin = 0; !done; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (spin > (1 << 22)) __trap();          // a lost TMA must fail loudly, never hang the GPU
-    }
-}
-// 3-D tiled load: box -> dense shared memory, completion counted in bytes on `bar`
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
-
-// L2 prefetch of a box (no shared-memory destination, no barrier): warms the tile a later CTA will stage
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2)
-{
-    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-
-// ---------------------------------------------------------------------------------------------
-// K3+K4: fused apply (+ inverse colour) + median.
-// ---------------------------------------------------------------------------------------------
-constexpr int TILE_W = 120;            // output pixels per tile row
-constexpr int BOX_W = 128;             // staged pixels per row: 4 left + 120 + 4 right
-constexpr int LPAD = 4;
-#ifndef RV_TILE_H
-#define RV_TILE_H 48
-#endif
-constexpr int TILE_H = RV_TILE_H;
-constexpr int HALF = TILE_H / 2;       // u16x2 lanes of the median hold rows (s, s + HALF)
-#ifndef RV_CHAIN_THREADS
-#define RV_CHAIN_THREADS 256
-#endif
-constexpr int CHAIN_THREADS = RV_CHAIN_THREADS;
-constexpr int CHAIN_WARPS = CHAIN_THREADS / 32;
-constexpr int A_STRIDE = BOX_W * 3 + 16; // bytes per staged BGR row: the box starts at the 16-byte boundary at or below
-                                       // pixel x0-LPAD (a TMA box must start 16-byte aligned), so up to 12 bytes of slack
-constexpr int P_STRIDE = BOX_W;        // words per plane row (one u16x2 word per pixel)
-constexpr int O_STRIDE = TILE_W * 3;   // bytes per output staging row
-constexpr int MAXQ = 6;                // quad tables kept in shared memory per CTA
-
-struct ChainArgs {
-    const uint8_t *src; size_t spitch, sfstride;
-    uint8_t *dst; size_t dpitch, dfstride;
-    Geo g;
-    const uint32_t *quads;             // [frames][(grid+1)^2][256]
-    const int32_t *flags;              // optional per-frame gate flags (0 = skip frame)
-    int use_tma;                       // stage the box with one cp.async.bulk.tensor per CTA (aligned buffers)
-    int prefetch_dist;                 // > 0: also prefetch into L2 the box of the CTA this many linear block ids ahead (the
-                                       // one that takes this CTA's place on the SM), so its staging wait is an L2 hit
-    const float *colp;                 // per 4-pixel box group: xa[4], xa1[4], -2^23 xa[4], -2^23 xa1[4], quad column[4]
-    // optional fused detector-input stage (integer down-scale letterbox, see k_letterbox): 0 = off
-    uint16_t *lb_out;                  // [frames][3][lb_S][lb_S] halves, RGB planes, value/255
-    int lb_scale, lb_S, lb_top, lb_left;
-    int write_full;                    // also store the full-resolution BGR result to dst
-};
-
-template <int K> struct MedianCfg;
-template <> struct MedianCfg<0> { static constexpr int M = 4; };
-template <> struct MedianCfg<3> { static constexpr int M = RV_MEDIAN3_M; };
-template <> struct MedianCfg<5> { static constexpr int M = RV_MEDIAN5_M; };
-template <> struct MedianCfg<7> { static constexpr int M = RV_MEDIAN7_M; };
-template <> struct MedianCfg<9> { static constexpr int M = RV_MEDIAN9_M; };
-
-template <int K, int NC, int M>
-__device__ __forceinline__ void median_net(const uint32_t (&v)[NC][K], uint32_t (&out)[M])
-{
-    if constexpr (K == 3) rv_median3_net(v, out);
-    else if constexpr (K == 5) rv_median5_net(v, out);
-    else if constexpr (K == 7) rv_median7_net(v, out);
-    else rv_median9_net(v, out);
-}
-
-template <int MODE, int K>
-struct ChainSmem {
-    static constexpr int R = K / 2;
-    static constexpr int BOX_H = TILE_H + 2 * R;
-    static constexpr int NSLOT = HALF + 2 * R;
-    static constexpr size_t a_bytes = (size_t)BOX_H * A_STRIDE;
-    static constexpr size_t p_bytes = K > 0 ? (size_t)3 * NSLOT * P_STRIDE * 4 : (size_t)TILE_H * O_STRIDE;  // K==0: output staging
-    static constexpr size_t row_bytes = (size_t)BOX_H * 16;
-    static constexpr size_t q_bytes = MODE == 2 ? 0 : (size_t)MAXQ * 256 * 4;
-    static constexpr size_t t_bytes = MODE == 1 ? sizeof(LabTabs) : MODE == 0 ? sizeof(YccTabs) : 0;
-    static constexpr size_t off_a = 0;
-    static constexpr size_t off_p = (a_bytes + 15) & ~(size_t)15;
-    static constexpr size_t off_row = off_p + ((p_bytes + 15) & ~(size_t)15);
-    static constexpr size_t off_q = off_row + row_bytes;
-    static constexpr size_t off_t = off_q + q_bytes;
-    static constexpr size_t total = off_t + t_bytes;
-};
-
-// MODE: 0 = CLAHE in YCrCb, 1 = CLAHE in LAB, 2 = no CLAHE (median only).  K: 0 (no median), 3, 5, 7, 9.
-#ifndef RV_CHAIN_MIN_CTAS
-#define RV_CHAIN_MIN_CTAS 2
-#endif
-template <int MODE, int K>
-__global__ void __launch_bounds__(CHAIN_THREADS, (K <= 5 ? RV_CHAIN_MIN_CTAS : 1))
-k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
-{
-    using S = ChainSmem<MODE, K>;
-    constexpr int R = S::R, BOX_H = S::BOX_H;
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t tma_bar;
-    uint8_t *A = smem + S::off_a;
-    uint32_t *P = reinterpret_cast<uint32_t *>(smem + S::off_p);
-    float4 *rowp = reinterpret_cast<float4 *>(smem + S::off_row);
-    uint32_t *Qs = reinterpret_cast<uint32_t *>(smem + S::off_q);
-    const LabTabs *tabs = reinterpret_cast<const LabTabs *>(smem + S::off_t);
-    uint8_t *O = K > 0 ? A : reinterpret_cast<uint8_t *>(P);       // output staging
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int f = blockIdx.z;
-    if (a.flags != nullptr && a.flags[f] == 0) return;            // gated-off frame: k_gate_copy handles it
-    const Geo g = a.g;
-    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
-    const uint8_t *frame = a.src + (size_t)f * a.sfstride;
-
-    // ---- phase 0: stage the BGR box: rows y0-R .. y0-R+BOX_H-1 (rows outside the frame are never read:
-    // compute_row clamps the row index = BORDER_REPLICATE of the later median); bytes from the 16-byte boundary
-    // at or below 3*(x0-LPAD) (`aoff` bytes of slack, 4 or 12), A_STRIDE bytes per row.
-    const int aoff = (3 * (x0 - LPAD)) & 15;
-    const int bx0 = 3 * (x0 - LPAD) - aoff;                       // first staged byte of each row (may be < 0)
-    if (a.use_tma) {
-        // one TMA box per CTA: 100 u32 x BOX_H rows of frame f; out-of-range parts are zero-filled by the hardware
-        if (tid == 0) mbar_init(&tma_bar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&tma_bar, (uint32_t)(BOX_H * A_STRIDE));
-            tma_load_3d(A, &tmap, &tma_bar, bx0 / 4, y0 - R, f);
-            if (a.prefetch_dist > 0) {
-                const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) + (unsigned)a.prefetch_dist;
-                const unsigned per_frame = gridDim.x * gridDim.y;
-                const unsigned nf = lin / per_frame, rem = lin - nf * per_frame;
-                const unsigned ny = rem / gridDim.x, nx = rem - ny * gridDim.x;
-                if (nf < gridDim.z) {
-                    const int nbx = 3 * ((int)nx * TILE_W - LPAD);
-                    tma_prefetch_3d(&tmap, (nbx - (nbx & 15)) / 4, (int)ny * TILE_H - R, (int)nf);
-                }
-            }
-        }
-    } else {
-        const int rowbytes = 3 * g.W;
-        const bool al4 = ((reinterpret_cast<uintptr_t>(frame) & 3) == 0) && (a.spitch % 4 == 0);
-        constexpr int WPR = A_STRIDE / 4;                         // 100 words per staged row
-        const bool full = al4 && bx0 >= 0 && bx0 + A_STRIDE <= rowbytes;
-        for (int ry = warp; ry < BOX_H; ry += CHAIN_WARPS) {
-            const int gy = y0 - R + ry;
-            if (gy < 0 || gy >= g.H) continue;
-            const uint8_t *rp = frame + (size_t)gy * a.spitch + bx0;
-            uint32_t *ar = reinterpret_cast<uint32_t *>(A + ry * A_STRIDE);
-            if (full) {
-                const uint32_t *rw = reinterpret_cast<const uint32_t *>(rp);
-                const uint32_t v0 = __ldg(rw + lane), v1 = __ldg(rw + lane + 32), v2 = __ldg(rw + lane + 64);
-                ar[lane] = v0; ar[lane + 32] = v1; ar[lane + 64] = v2;
-                if (lane + 96 < WPR) ar[lane + 96] = __ldg(rw + lane + 96);
-            } else {
-                for (int wx = lane; wx < WPR; wx += 32) {
-                    const int b = bx0 + 4 * wx;
-                    uint32_t v = 0;
-                    if (al4 && b >= 0 && b + 4 <= rowbytes) {
-                        v = __ldg(reinterpret_cast<const uint32_t *>(rp + 4 * wx));
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (b + k >= 0 && b + k < rowbytes) v |= (uint32_t)rp[4 * wx + k] << (8 * k);
-                    }
-                    ar[wx] = v;
-                }
-            }
-        }
-    }
-    // interpolation terms of this lane's four pixels (A.3), evaluated at the clamped coordinate.  They depend only on
-    // the column, so the host builds them once per (W, tile width) with the same IEEE single-precision operations
-    // (rv_b200.cu: build_colparams) and each lane fetches its five 16-byte records.
-    float xa[4], xa1[4], cxa[4], cxa1[4];
-    int qxl[4], qcol[4];
-    int qx_lo = 0, nqx = 1, qy_lo = 0;
-    bool q_smem = true;
-    const bool lane_inside = (x0 - LPAD + 4 * lane >= 0) && (x0 - LPAD + 4 * lane + 3 < g.W);
-    if (MODE != 2) {
-        auto qof = [](int p, float inv) { return (int)floorf(__fsub_rn(__fmul_rn((float)p, inv), 0.5f)) + 1; };
-        const int cy_first = min(max(y0 - R, 0), g.H - 1), cy_last = min(max(y0 - R + BOX_H - 1, 0), g.H - 1);
-        const int gbase = (TILE_W / 4) * blockIdx.x;              // record of lane 0 (box group x0/4 - 1, stored at +1)
-        {
-            const float4 *cp = reinterpret_cast<const float4 *>(a.colp) + 5 * (gbase + lane);
-            const float4 r0 = __ldg(cp), r1 = __ldg(cp + 1), r2 = __ldg(cp + 2), r3 = __ldg(cp + 3);
-            const int4 r4 = __ldg(reinterpret_cast<const int4 *>(cp + 4));
-            xa[0] = r0.x; xa[1] = r0.y; xa[2] = r0.z; xa[3] = r0.w;
-            xa1[0] = r1.x; xa1[1] = r1.y; xa1[2] = r1.z; xa1[3] = r1.w;
-            cxa[0] = r2.x; cxa[1] = r2.y; cxa[2] = r2.z; cxa[3] = r2.w;
-            cxa1[0] = r3.x; cxa1[1] = r3.y; cxa1[2] = r3.z; cxa1[3] = r3.w;
-            qxl[0] = r4.x; qxl[1] = r4.y; qxl[2] = r4.z; qxl[3] = r4.w;
-        }
-        qx_lo = __ldg(reinterpret_cast<const int *>(a.colp) + 20 * gbase + 16);
-        nqx = __ldg(reinterpret_cast<const int *>(a.colp) + 20 * (gbase + 31) + 19) - qx_lo + 1;
-        qy_lo = qof(cy_first, g.inv_th);
-        const int nqy = qof(cy_last, g.inv_th) - qy_lo + 1;
-        const int nq = nqx * nqy;
-        q_smem = nq <= MAXQ;
-        const uint32_t *qf = a.quads + (size_t)f * (g.grid + 1) * (g.grid + 1) * 256;
-        if (q_smem) {
-            // lq / nqx without an integer division: lq < nq <= MAXQ = 6, so (lq * ceil(256 / nqx)) >> 8 is exact
-            const int rcp_b = (int)((0x2B3440568000ull >> (8 * (nqx - 1))) & 0xFF);   // ceil(256 / nqx) for nqx = 2..6; 0 for 1
-            const int rcp = rcp_b ? rcp_b : 256;
-            for (int i = tid; i < nq * 64; i += CHAIN_THREADS) {   // 64 x 16 bytes per quad table
-                const int lq = i >> 6, v4 = i & 63;
-                const int dq = (lq * rcp) >> 8;
-                const int qy = qy_lo + dq, qx = qx_lo + lq - dq * nqx;
-                reinterpret_cast<uint4 *>(Qs)[i] = __ldg(reinterpret_cast<const uint4 *>(qf + ((size_t)qy * (g.grid + 1) + qx) * 256) + v4);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            qxl[j] -= qx_lo;
-            qcol[j] = qxl[j] << 8;
-        }
-        for (int ry = tid; ry < BOX_H; ry += CHAIN_THREADS) {
-            const int gy = min(max(y0 - R + ry, 0), g.H - 1);
-            const float tyf = __fsub_rn(__fmul_rn((float)gy, g.inv_th), 0.5f);
-            const float fl = floorf(tyf);
-            const float ya = __fsub_rn(tyf, fl);
-            const int qy = (int)fl + 1;
-            rowp[ry] = make_float4(ya, __fsub_rn(1.0f, ya), __int_as_float(q_smem ? (((qy - qy_lo) * nqx) << 8) : qy),
-                                   __int_as_float((gy - (y0 - R)) * A_STRIDE));
-        }
-        if (MODE == 1) copy_lab_tabs(const_cast<LabTabs *>(tabs));
-        if (MODE == 0) {
-            const uint4 *ys = reinterpret_cast<const uint4 *>(&g_ycc);
-            uint4 *yd = reinterpret_cast<uint4 *>(smem + S::off_t);
-            for (int i = tid; i < (int)(sizeof(YccTabs) / 16); i += CHAIN_THREADS) yd[i] = __ldg(ys + i);
-        }
-    }
-    if (a.use_tma && warp == 0) mbar_wait(&tma_bar, 0);     // one warp polls the mbarrier; the others sleep in the barrier below
-    __syncthreads();
-
-    // ---- phase 1: CLAHE on the luminance of every staged pixel (or plain unpack when MODE == 2)
-    const uint32_t *qglob = (MODE != 2) ? a.quads + (size_t)f * (g.grid + 1) * (g.grid + 1) * 256 : nullptr;
-    // YCrCb results are produced UNCLAMPED with RV_BIAS16 added (K > 0): the saturation to [0,255] happens on the
-    // packed u16x2 plane words (two values per VIMNMX.S16x2) instead of per value; LAB / passthrough values are exact.
-    constexpr bool RAW = (MODE == 0) && (K > 0);
-    const uint32_t ycc_s = smem_u32(smem + S::off_t);            // shared-memory address of the chroma tables (MODE 0)
-    // phase 1 is instantiated twice (quad tables in shared memory / fetched from global) and the CTA-uniform choice is
-    // made once, outside: a predicated dual path costs issue slots for every masked-off address instruction.
-    auto phase1 = [&](auto QS) {
-    constexpr bool q_in_smem = decltype(QS)::value;
-    auto compute_row = [&](int ry, int (&o)[12]) {
-        int Bv[4], Gv[4], Rv[4];
-        float4 rp;
-        const uint8_t *ar;
-        if (MODE == 2) {
-            ar = A + (min(max(y0 - R + ry, 0), g.H - 1) - (y0 - R)) * A_STRIDE;
-        } else {
-            rp = rowp[ry];
-            ar = A + __float_as_int(rp.w);                 // staged row of the clamped image row
-        }
-        uint32_t px[4];                                    // (B, G, R, x) of each pixel in one word
-        if (lane_inside) {
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(ar + aoff + 12 * lane);
-            const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
-            px[0] = w0; px[1] = __funnelshift_r(w0, w1, 24); px[2] = __funnelshift_r(w1, w2, 16); px[3] = w2 >> 8;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                Bv[j] = px[j] & 255;
-                Gv[j] = __byte_perm(px[j], 0, 0x4441);
-                Rv[j] = __byte_perm(px[j], 0, 0x4442);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int cx = min(max(x0 - LPAD + 4 * lane + j, 0), g.W - 1);
-                const uint8_t *p = ar + aoff + 3 * (cx - (x0 - LPAD));
-                Bv[j] = p[0]; Gv[j] = p[1]; Rv[j] = p[2];
-                px[j] = (uint32_t)Bv[j] | ((uint32_t)Gv[j] << 8) | ((uint32_t)Rv[j] << 16);
-            }
-        }
-        if (MODE == 2) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { o[j] = Bv[j]; o[4 + j] = Gv[j]; o[8 + j] = Rv[j]; }
-            return;
-        }
-        const float ya = rp.x, ya1 = rp.y;
-        int ly[4], lx[4], lz[4];                                 // LAB: y and the two XZ arguments of the four pixels
-        const int qrow = __float_as_int(rp.z);                    // (local quad row * quads per row) << 8, or the global row
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int L, c1 = 0, c2 = 0;
-            uint32_t eB = 0, eR = 0;
-            if (MODE == 1) {
-                lab_fwd(tabs, Bv[j], Gv[j], Rv[j], L, c1, c2);
-            } else {
-                // A.1 forward: Y from the packed pixel word; the chroma round trip comes from the tables (see YccTabs):
-                // entries of d = B - Y and d = R - Y
-                L = (int)luma_y(px[j]);
-                // one shared term (table base - 4 Y) for both look-ups; the empty asm keeps the compiler from re-associating it
-                // into a subtraction per channel.  The tables are constant after the barrier above and the address depends on
-                // this pixel, so a plain (non-volatile) shared load is safe.
-                uint32_t yrow = ycc_s + 4u * 255u - 4u * (uint32_t)L;
-                asm("" : "+r"(yrow));
-                asm("ld.shared.u32 %0, [%1];" : "=r"(eB) : "r"(yrow + 4u * (uint32_t)Bv[j]));
-                asm("ld.shared.u32 %0, [%1+2048];" : "=r"(eR) : "r"(yrow + 4u * (uint32_t)Rv[j]));
-            }
-            uint32_t q;
-            if constexpr (q_in_smem) q = Qs[qrow + qcol[j] + L];
-            else q = __ldg(qglob + (((size_t)qrow * (g.grid + 1) + (qxl[j] + qx_lo)) << 8) + L);
-            // 0x4B0000vv = 2^23 + vv ; fma(2^23 + v, w, -2^23 * w) == v * w rounded once (A.3: no FMA contraction
-            // between the products and the sums -- each step below is individually rounded)
-            const float m00 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7440));
-            const float m01 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7441));
-            const float m10 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7442));
-            const float m11 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7443));
-            const float p00 = __fmaf_rn(m00, xa1[j], cxa1[j]);
-            const float p01 = __fmaf_rn(m01, xa[j], cxa[j]);
-            const float p10 = __fmaf_rn(m10, xa1[j], cxa1[j]);
-            const float p11 = __fmaf_rn(m11, xa[j], cxa[j]);
-            const float top = __fmul_rn(__fadd_rn(p00, p01), ya1);
-            const float bot = __fmul_rn(__fadd_rn(p10, p11), ya);
-            const float res = __fadd_rn(top, bot);
-            // round-half-even via the 1.5*2^23 trick; res <= 255*(1 + 1e-6), so the result is already in [0,255]
-            // RAW: the bias 0x6400 rides along in the magic constant and the float's upper bits are left in place; only the
-            // low 16 bits of the sums below are ever used (pack2 keeps the low halves), so no masking is needed.
-            // YCrCb: - 256 because the tables' f fields and the G sum carry + 256.
-            constexpr float MAGIC = 12582912.0f + (RAW ? 25600.0f : 0.0f) - (MODE == 0 ? 256.0f : 0.0f);
-            const int Lw = __float_as_int(__fadd_rn(res, MAGIC));
-            if (MODE == 1) {
-                lab_inv_args(tabs, Lw & 0x1FF, c1, c2, ly[j], lx[j], lz[j]);
-            } else {
-                // A.1 inverse: B' = Y' + fB, G' = Y' + ((tB + tR + 8192) >> 14), R' = Y' + fR
-                const int L2 = RAW ? Lw : (Lw << 16) >> 16;          // non-RAW: sign-extended Y' - 256
-                const int bb = L2 + (int)(eB >> 22);
-                const int gg = L2 + (int)(((eB + eR) << 10) >> 23);
-                const int rr = L2 + (int)(eR >> 22);
-                if (RAW) { o[j] = bb; o[4 + j] = gg; o[8 + j] = rr; }
-                else { o[j] = sat8(bb); o[4 + j] = sat8(gg); o[8 + j] = sat8(rr); }
-            }
-        }
-        if (MODE == 1) {
-            const int lowest = min(min(min(lx[0], lz[0]), min(lx[1], lz[1])), min(min(lx[2], lz[2]), min(lx[3], lz[3])));
-            if (__any_sync(0xffffffffu, lowest <= 3390)) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) lab_inv_tail<false>(tabs, ly[j], lx[j], lz[j], o[j], o[4 + j], o[8 + j]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) lab_inv_tail<true>(tabs, ly[j], lx[j], lz[j], o[j], o[4 + j], o[8 + j]);
-            }
-        }
-    };
-    // two rows' values of one pixel/channel -> one plane word (low half = first row), saturated and biased
-    auto pack2 = [&](int lo, int hi) -> uint32_t {
-        const uint32_t w = __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
-        if (RAW) return __vmins2(__vmaxs2(w, RV_PLANE_BIAS), RV_PLANE_BIAS | 0x00FF00FFu);
-        return w | RV_PLANE_BIAS;
-    };
-
-    if constexpr (K == 0) {
-        // no median: write the interleaved result straight to the staging tile (lanes 0 and 31 hold halo only)
-        for (int ry = warp; ry < TILE_H; ry += CHAIN_WARPS) {
-            if (y0 + ry >= g.H) break;
-            int o[12];
-            compute_row(ry, o);                      // all 32 lanes: compute_row votes across the warp (LAB inverse)
-            if (lane >= 1 && lane <= 30) {
-                uint32_t *op = reinterpret_cast<uint32_t *>(O + ry * O_STRIDE + 12 * (lane - 1));
-                op[0] = (uint32_t)o[0] | ((uint32_t)o[4] << 8) | ((uint32_t)o[8] << 16) | ((uint32_t)o[1] << 24);
-                op[1] = (uint32_t)o[5] | ((uint32_t)o[9] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[6] << 24);
-                op[2] = (uint32_t)o[10] | ((uint32_t)o[3] << 8) | ((uint32_t)o[7] << 16) | ((uint32_t)o[11] << 24);
-            }
-        }
-    } else {
-        // planes P[c][slot][px]: low half = row `slot`, high half = row `slot + HALF` of the box
-        constexpr int NSLOT = S::NSLOT;
-        for (int s = warp; s < HALF; s += CHAIN_WARPS) {
-            int o0[12], o1[12];
-            compute_row(s, o0);
-            compute_row(s + HALF, o1);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                uint4 w;
-                w.x = pack2(o0[4 * c + 0], o1[4 * c + 0]);
-                w.y = pack2(o0[4 * c + 1], o1[4 * c + 1]);
-                w.z = pack2(o0[4 * c + 2], o1[4 * c + 2]);
-                w.w = pack2(o0[4 * c + 3], o1[4 * c + 3]);
-                *reinterpret_cast<uint4 *>(P + (c * NSLOT + s) * P_STRIDE + 4 * lane) = w;
-            }
-            if (s < 2 * R) {       // rows [HALF, HALF+2R) are also the low half of slots [HALF, HALF+2R)
-                compute_row(s + TILE_H, o0);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    uint4 w;
-                    w.x = pack2(o1[4 * c + 0], o0[4 * c + 0]);
-                    w.y = pack2(o1[4 * c + 1], o0[4 * c + 1]);
-                    w.z = pack2(o1[4 * c + 2], o0[4 * c + 2]);
-                    w.w = pack2(o1[4 * c + 3], o0[4 * c + 3]);
-                    *reinterpret_cast<uint4 *>(P + (c * NSLOT + s + HALF) * P_STRIDE + 4 * lane) = w;
-                }
-            }
-        }
-    }
-    };   // phase1
-    if (q_smem) phase1(std::true_type{}); else phase1(std::false_type{});
-    __syncthreads();
-
-    // ---- phase 2: k x k median per channel plane; lanes of each u16x2 are output rows (s, s+HALF)
-    constexpr bool TWO_ROW = (K == 5 && RV_MEDIAN5_2ROW) || (K == 3 && RV_MEDIAN3_2ROW);
-    if constexpr (TWO_ROW) {
-        // two vertically adjacent output rows per task (slots s, s+1): the K-1 middle window rows are shared
-        constexpr int NSLOT = S::NSLOT;
-        constexpr int M = (K == 5) ? RV_MEDIAN5X2_M : RV_MEDIAN3X2_M;
-        constexpr int NG = TILE_W / M;
-        constexpr int NC = M + K - 1;
-        constexpr int NR = K + 1;                    // plane rows per task
-        constexpr int C0 = LPAD - R;                 // first needed plane word, relative to the group's first output
-        static_assert((M == 4 || M == 6) && TILE_W % M == 0 && HALF % 2 == 0, "two-row median layout");
-        // task = (row pair sp, channel c, group m), m fastest; a thread's next task is CHAIN_THREADS further on.  The three
-        // coordinates are carried incrementally (one division per thread instead of four per task).
-        constexpr int DM = CHAIN_THREADS % NG, DT = CHAIN_THREADS / NG, DC = DT % 3, DSP = DT / 3;
-        int m = tid % NG, c = (tid / NG) % 3, sp = (tid / NG) / 3;
-        for (; sp < HALF / 2; ) {
-            const int s = 2 * sp;
-            const bool live = (x0 + M * m < g.W) && (y0 + s < g.H);
-            const int mo = m, co = c;
-            // advance to this thread's next task
-            m += DM; c += DC; sp += DSP;
-            if (m >= NG) { m -= NG; ++c; }
-            if (c >= 3) { c -= 3; ++sp; }
-            if constexpr (DC + 1 >= 3) { if (c >= 3) { c -= 3; ++sp; } }
-            if (!live) continue;
-            uint32_t v[NC][NR];
-            const uint32_t *pc = P + (co * NSLOT + s) * P_STRIDE;
-            if constexpr (M == 4) {
-#pragma unroll
-                for (int d = 0; d < NR; ++d) {
-                    const uint4 *p4 = reinterpret_cast<const uint4 *>(pc + d * P_STRIDE + 4 * mo);
-                    const uint4 q0 = p4[0], q1 = p4[1], q2 = p4[2];
-                    const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-#pragma unroll
-                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[C0 + cc];
-                }
-            } else if constexpr (M % 2 == 0) {
-                // 8-byte loads from the even word at or below the first needed column (k = 3: one unused leading word);
-                // with M = 6 the 16 lanes of a phase hit 16 distinct even banks (6m + 2 mod 32): conflict-free
-                constexpr int C0E = C0 & ~1, SKIP = C0 - C0E, NW = (SKIP + NC + 1) / 2;
-#pragma unroll
-                for (int d = 0; d < NR; ++d) {
-                    const uint2 *p2 = reinterpret_cast<const uint2 *>(pc + d * P_STRIDE + M * mo + C0E);
-                    uint32_t w[2 * NW];
-#pragma unroll
-                    for (int cc = 0; cc < NW; ++cc) {
-                        const uint2 q = p2[cc];
-                        w[2 * cc] = q.x; w[2 * cc + 1] = q.y;
-                    }
-#pragma unroll
-                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[SKIP + cc];
-                }
-            } else {
-#pragma unroll
-                for (int d = 0; d < NR; ++d)
-#pragma unroll
-                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = pc[d * P_STRIDE + M * mo + C0 + cc];
-            }
-            uint32_t out[2][M];
-            if constexpr (K == 5) rv_median5x2_net(v, out);
-            else rv_median3x2_net(v, out);
-#pragma unroll
-            for (int hrow = 0; hrow < 2; ++hrow) {
-                uint8_t *o0 = O + (s + hrow) * O_STRIDE + 3 * M * mo + co;
-                uint8_t *o1 = o0 + HALF * O_STRIDE;
-#pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    o0[3 * j] = (uint8_t)(out[hrow][j] & 255);
-                    o1[3 * j] = (uint8_t)((out[hrow][j] >> 16) & 255);
-                }
-            }
-        }
-        __syncthreads();
-    } else if constexpr (K > 0) {
-        constexpr int NSLOT = S::NSLOT;
-        constexpr int M = MedianCfg<K>::M;
-        constexpr int NG = TILE_W / M;               // output groups per row
-        constexpr int NC = M + K - 1;                // pixel columns per group
-        for (int task = tid; task < 3 * NG * HALF; task += CHAIN_THREADS) {
-            const int m = task % NG;
-            const int t2 = task / NG;
-            const int c = t2 % 3, s = t2 / 3;
-            if (x0 + M * m >= g.W) continue;
-            if (y0 + s >= g.H) continue;
-            uint32_t v[NC][K];
-            const uint32_t *pc = P + (c * NSLOT + s) * P_STRIDE;
-            constexpr int C0 = LPAD - R;                 // first needed plane word, relative to the group's first output
-            if constexpr (M == 4) {
-                // 16-byte loads of words 4m .. 4m+11 (conflict-free: 8 lanes x 16 B per phase)
-#pragma unroll
-                for (int d = 0; d < K; ++d) {
-                    const uint4 *p4 = reinterpret_cast<const uint4 *>(pc + d * P_STRIDE + 4 * m);
-                    const uint4 q0 = p4[0], q1 = p4[1], q2 = p4[2];
-                    const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-#pragma unroll
-                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[C0 + cc];
-                }
-            } else if constexpr (C0 % 2 == 0 && M % 2 == 0 && NC % 2 == 0) {
-                // 8-byte loads; with M = 6 the 16 lanes of a phase hit 16 distinct even banks (6m+2 mod 32)
-#pragma unroll
-                for (int d = 0; d < K; ++d) {
-                    const uint2 *p2 = reinterpret_cast<const uint2 *>(pc + d * P_STRIDE + M * m + C0);
-#pragma unroll
-                    for (int cc = 0; cc < NC / 2; ++cc) {
-                        const uint2 q = p2[cc];
-                        v[2 * cc][d] = q.x; v[2 * cc + 1][d] = q.y;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int d = 0; d < K; ++d)
-#pragma unroll
-                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = pc[d * P_STRIDE + M * m + C0 + cc];
-            }
-            uint32_t out[M];
-            median_net<K, NC, M>(v, out);
-            uint8_t *o0 = O + s * O_STRIDE + 3 * M * m + c;
-            uint8_t *o1 = o0 + HALF * O_STRIDE;
-#pragma unroll
-            for (int j = 0; j < M; ++j) {
-                o0[3 * j] = (uint8_t)(out[j] & 255);
-                o1[3 * j] = (uint8_t)((out[j] >> 16) & 255);
-            }
-        }
-        __syncthreads();
-    } else {
-        __syncthreads();
-    }
-
-    // ---- phase 3: coalesced store of the staging tile (one warp per row, three words per lane)
-    if (a.write_full) {
-        uint8_t *dframe = a.dst + (size_t)f * a.dfstride;
-        const int nb = min(3 * TILE_W, 3 * (g.W - x0));          // valid bytes per row
-        const bool al4 = ((reinterpret_cast<uintptr_t>(dframe) & 3) == 0) && (a.dpitch % 4 == 0);
-        const int rows = min(TILE_H, g.H - y0);
-        constexpr int WPR = O_STRIDE / 4;                        // 90 words per row
-        const bool al8 = ((reinterpret_cast<uintptr_t>(dframe) & 7) == 0) && (a.dpitch % 8 == 0);
-        if (al8 && nb == 3 * TILE_W && rows == TILE_H) {
-            // full tile, 8-byte aligned rows (3*x0 = 360*bx): 45 double words per row, four rows per warp, fully unrolled
-            uint8_t *dp = dframe + (size_t)(y0 + warp) * a.dpitch + 3 * (size_t)x0 + 8 * lane;
-            const uint8_t *op = O + warp * O_STRIDE + 8 * lane;
-            const size_t dstep = (size_t)CHAIN_WARPS * a.dpitch;
-#pragma unroll
-            for (int k = 0; k < TILE_H / CHAIN_WARPS; ++k) {
-                const uint2 v0 = *reinterpret_cast<const uint2 *>(op);
-                *reinterpret_cast<uint2 *>(dp) = v0;
-                if (lane < 45 - 32) *reinterpret_cast<uint2 *>(dp + 256) = *reinterpret_cast<const uint2 *>(op + 256);
-                dp += dstep;
-                op += CHAIN_WARPS * O_STRIDE;
-            }
-        } else
-        for (int ry = warp; ry < rows; ry += CHAIN_WARPS) {
-            uint8_t *dp = dframe + (size_t)(y0 + ry) * a.dpitch + 3 * (size_t)x0;
-            const uint32_t *orow = reinterpret_cast<const uint32_t *>(O + ry * O_STRIDE);
-            if (al4 && nb == 3 * TILE_W) {
-                uint32_t *dw = reinterpret_cast<uint32_t *>(dp);
-                const uint32_t v0 = orow[lane], v1 = orow[lane + 32];
-                dw[lane] = v0; dw[lane + 32] = v1;
-                if (lane + 64 < WPR) dw[lane + 64] = orow[lane + 64];
-            } else {
-                for (int wx = lane; wx < WPR; wx += 32) {
-                    const int b = 4 * wx;
-                    if (b >= nb) break;
-                    const uint32_t v = orow[wx];
-                    if (al4 && b + 4 <= nb) *reinterpret_cast<uint32_t *>(dp + b) = v;
-                    else for (int k = 0; k < 4 && b + k < nb; ++k) dp[b + k] = (uint8_t)(v >> (8 * k));
-                }
-            }
-        }
-    }
-    // ---- phase 3b (optional): detector input.  Integer down-scale s: cv2.resize(INTER_LINEAR) degenerates to the
-    // centre pixel (odd s) or the rounded mean of the centre 2x2 block (even s; = the fixed-point formula with both
-    // weights 1024), which never straddles a tile because tile sizes are even and multiples of s are tile aligned in x.
-    if (a.lb_out != nullptr) {
-        const int sc = a.lb_scale, S = a.lb_S;
-        const int off = (sc - 1) >> 1;                           // first source pixel of output d is sc*d + off
-        const int nw = g.W / sc, nh = g.H / sc;
-        const int dx0 = (x0 - off + sc - 1) / sc;                // outputs whose first source column is in this tile
-        const int dx1 = min((x0 + TILE_W - 1 - off) / sc, nw - 1);
-        const int dy0 = (y0 - off + sc - 1) / sc;
-        const int dy1 = min((y0 + TILE_H - 1 - off) / sc, nh - 1);
-        const int ncol = dx1 - dx0 + 1, nrow = dy1 - dy0 + 1;
-        if (ncol > 0 && nrow > 0) {
-            uint16_t *ob = a.lb_out + (size_t)f * 3 * S * S;
-            const bool even = (sc & 1) == 0;
-            for (int i = tid; i < ncol * nrow; i += CHAIN_THREADS) {
-                const int ry = i / ncol, rx = i - ry * ncol;
-                const int dy = dy0 + ry, dx = dx0 + rx;
-                const uint8_t *p = O + (sc * dy + off - y0) * O_STRIDE + 3 * (sc * dx + off - x0);
-                int v[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (even) v[c] = (p[c] + p[c + 3] + p[c + O_STRIDE] + p[c + O_STRIDE + 3] + 2) >> 2;
-                    else v[c] = p[c];
-                }
-                uint16_t *o = ob + (size_t)(a.lb_top + dy) * S + a.lb_left + dx;
-#pragma unroll
-                for (int c = 0; c < 3; ++c)                      // planes are R, G, B; staging is B, G, R
-                    o[(size_t)(2 - c) * S * S] = __half_as_ushort(__float2half_rn(__fdiv_rn((float)v[c], 255.0f)));
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Detector-input stage, general form: letterbox to S x S with cv2.resize(INTER_LINEAR) 8-bit
-// fixed-point arithmetic (coefficients scaled by 2048, tables built on the host exactly as OpenCV builds them),
-// constant padding, BGR->RGB, HWC->CHW, /255, fp16.  grid (ceil(S/32), ceil(S/8), frames), block (32, 8).
-// only_pad = 1 writes just the padding (the image rectangle is produced by k_chain's fused phase 3b).
-// ---------------------------------------------------------------------------------------------
-struct LbArgs {
-    const uint8_t *src; size_t spitch, sfstride;
-    uint16_t *out;
-    int H, W, S, nw, nh, top, left, pad, only_pad;
-    const int32_t *xofs;     // [nw] first source column (already clamped)
-    const int16_t *xa;       // [nw][2]
-    const int32_t *yofs;     // [nh][2] both source rows (clamped)
-    const int16_t *ya;       // [nh][2]
-};
-
-__global__ void __launch_bounds__(256) k_letterbox(const LbArgs a)
-{
-    const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y, f = blockIdx.z;
-    if (dx >= a.S || dy >= a.S) return;
-    uint16_t *o = a.out + (size_t)f * 3 * a.S * a.S + (size_t)dy * a.S + dx;
-    const int ix = dx - a.left, iy = dy - a.top;
-    const size_t plane = (size_t)a.S * a.S;
-    if (ix < 0 || ix >= a.nw || iy < 0 || iy >= a.nh) {
-        const uint16_t pv = __half_as_ushort(__float2half_rn(__fdiv_rn((float)a.pad, 255.0f)));
-        o[0] = pv; o[plane] = pv; o[2 * plane] = pv;
-        return;
-    }
-    if (a.only_pad) return;
-    const int sx = a.xofs[ix], sx1 = min(sx + 1, a.W - 1);
-    const int a0 = a.xa[2 * ix], a1 = a.xa[2 * ix + 1];
-    const int b0 = a.ya[2 * iy], b1 = a.ya[2 * iy + 1];
-    const uint8_t *r0 = a.src + (size_t)f * a.sfstride + (size_t)a.yofs[2 * iy] * a.spitch;
-    const uint8_t *r1 = a.src + (size_t)f * a.sfstride + (size_t)a.yofs[2 * iy + 1] * a.spitch;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const int h0 = r0[3 * sx + c] * a0 + r0[3 * sx1 + c] * a1;       // horizontal pass, scaled by 2048
-        const int h1 = r1[3 * sx + c] * a0 + r1[3 * sx1 + c] * a1;
-        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;   // VResizeLinear<uchar,int,short>
-        o[(size_t)(2 - c) * plane] = __half_as_ushort(__float2half_rn(__fdiv_rn((float)min(max(v, 0), 255), 255.0f)));
-    }
-}
-
-}  // namespace rv
+#include "rv_common.cuh"
+#include "rv_colour.cuh"
+#include "rv_hist_lut.cuh"
+#include "rv_chain.cuh"
