@@ -257,6 +257,22 @@ def test_tma_and_plain_staging_agree(ctx):
         assert np.array_equal(a[i], O.chain(frames[i], O.SPACE_YCRCB, 2.0, 8, 5))
 
 
+def test_l2_prefetch_option_changes_nothing(ctx):
+    """Option "prefetch_ctas" (k_chain also prefetches a later CTA's box into L2; off by default) must not change a byte."""
+    import rvb200
+    from rvb200 import synth
+    frames = synth.frame_pool(360, 640, 5, base_seed=71)
+    p = rvb200.Params.make("LAB", 2.0, 8, 3)
+    a = ctx.chain(frames, p)
+    for dist in (1, 3, 1000):              # 1000: every prefetch target lies beyond the grid
+        ctx.set_option("prefetch_ctas", dist)
+        try:
+            b = ctx.chain(frames, p)
+        finally:
+            ctx.set_option("prefetch_ctas", 0)
+        assert np.array_equal(a, b), dist
+
+
 def test_letterbox_stage_and_fused_chain(ctx):
     """Detector-input stage: stand-alone letterbox and chain+letterbox, fused (integer scale: 1080p->640 /3,
     720p /2, 4K-ish /6) and unfused (ragged), all bit-exact in fp16 against the oracle restatement of cv2.resize."""
