@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Are the shipped two-row selection networks locally minimal?  For every min/max node of the live DAG, try to replace it by
 either of its operands and re-check all outputs on 40,000 vectors (wide range, heavy ties, 0/1 inputs).  A replacement that
-survives would be a removable operation.  Result on the shipped networks: none (5x5: 748 operations, 3x3: 212).
+survives would be a removable operation.  Result on the shipped networks: none (5x5: 740 operations, 3x3: 212).
     python tools/check_median_net_irredundant.py [5|3]"""
 import os
 import sys

@@ -300,7 +300,8 @@ def build5_2rows(M, parity, rparity=0):
     middle rows are shared.  Columns of the middle rows are sorted once (sort4), merged in pairs P4 and quads Q4
     (ranks 3..12 of 16 kept), joined with the fifth column (ranks 4..9 of 14 kept = the only ranks of the 20 shared
     elements that can be the median of 25); each output then takes the 6th smallest of those six and its own
-    sorted outer row window (sliding sort4 + insert, shared by horizontal neighbours)."""
+    sorted outer row window (sliding sort4 -- two ordered pairs merged, the pairs shared between groups -- + insert,
+    shared by horizontal neighbours)."""
     d = Dag()
     ncol = M + 4
     inp = [[d.inp((c, r)) for r in range(6)] for c in range(ncol)]
@@ -327,7 +328,9 @@ def build5_2rows(M, parity, rparity=0):
         if (r, o) not in rowwin:
             b = o if o % 2 == rparity else o - 1
             if b >= 0 and b + 5 < ncol:
-                c4 = d.sort([inp[c][r] for c in range(b + 1, b + 5)])
+                # sort4 as two ordered pairs merged: the pair (b+3, b+4) is also the first pair of the next group (b+2)
+                e = [inp[c][r] for c in range(b + 1, b + 5)]
+                c4 = d.merge(d.sort(e[:2]), d.sort(e[2:]))
                 rowwin[(r, b)] = d.merge([inp[b][r]], c4)
                 rowwin[(r, b + 1)] = d.merge([inp[b + 5][r]], c4)
             else:
