@@ -294,7 +294,6 @@ int launch_hist(rv_ctx *ctx, const uint8_t *src, size_t pitch, size_t fstride, c
                 int32_t *hist, uint8_t *luma, int32_t *mm, cudaStream_t st)
 {
     const int tiles = g.grid * g.grid;
-    CK(cudaMemsetAsync(hist, 0, (size_t)n * tiles * 256 * sizeof(int32_t), st));
     if (mm) {
         k_init_minmax<<<(n + 127) / 128, 128, 0, st>>>(mm, n);
         ctx->launches++;
@@ -305,6 +304,7 @@ int launch_hist(rv_ctx *ctx, const uint8_t *src, size_t pitch, size_t fstride, c
     if ((long)tiles * n < want) slices = (int)std::min<long>((want + (long)tiles * n - 1) / ((long)tiles * n), std::max(1, g.th / 8));
     const int rps = (g.th + slices - 1) / slices;
     slices = (g.th + rps - 1) / rps;
+    if (slices > 1) CK(cudaMemsetAsync(hist, 0, (size_t)n * tiles * 256 * sizeof(int32_t), st));
     dim3 grid(slices, tiles, n);
     {
         ScopedTiming tm(ctx, st, 0);

@@ -14,7 +14,8 @@ namespace rv {
 
 // ---------------------------------------------------------------------------------------------
 // K1: luminance + per-tile histograms
-// grid = (slices, tiles, frames), block = 256.  hist must be zeroed; slices accumulate with atomics.
+// grid = (slices, tiles, frames), block = 256.  With more than one slice per tile hist must be zeroed (the slices
+// accumulate with atomics); with one slice the CTA stores its bins.
 // ---------------------------------------------------------------------------------------------
 constexpr int HIST_THREADS = 256;
 constexpr int HIST_WARPS = HIST_THREADS / 32;
@@ -181,7 +182,9 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
         uint32_t s = 0;
 #pragma unroll
         for (int w = 0; w < HIST_WARPS; ++w) s += wh[w][tid];
-        if (s) atomicAdd(&hist[((size_t)f * g.grid * g.grid + tile) * 256 + tid], (int)s);
+        int32_t *bin = &hist[((size_t)f * g.grid * g.grid + tile) * 256 + tid];
+        if (gridDim.x == 1) *bin = (int)s;          // one CTA per tile: plain store, the buffer need not be zeroed
+        else if (s) atomicAdd(bin, (int)s);
     }
     if (want_gray) {
 #pragma unroll
