@@ -3,21 +3,27 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A step is one pass of the hot path (CLAHEDehaze -> MedianDerain) over one batch of synthetic fogged +
-rained frames.  Workload at every N: BASELINE.json configs[1] -- 1920x1080, batch 64 per GPU, YCrCb,
-clip 2.0, tile grid 8, median k5 (frames/streams shard across GPUs with no inter-GPU traffic, so N GPUs
-process N such batches: weak scaling).
+A step is one pass of the hot path (CLAHEDehaze -> MedianDerain) over one batch of fogged + rained frames.  Workload at
+every N: BASELINE.json configs[1] -- 1920x1080, batch 64 per GPU, YCrCb, clip 2.0, tile grid 8, median k5 (frames /
+streams shard across GPUs with no inter-GPU traffic, so N GPUs process N such batches: weak scaling).  The frame pool
+is eight frames made by the reference's own fog synthesiser (tests/golden/pool_1080p, tools/fog_batch.py parameters).
 
-`value`  : frames/s with inputs and outputs resident in HBM (CUDA events, max over ranks).
-`e2e`    : same metric through the public plugin API (PreprocessPipeline.process_batch) from pinned host
-           buffers, H2D and D2H inside the timed region.
-`roofline`: the dominant kernel (k_chain) against the measured HBM copy bandwidth; its time is measured
-           live with CUDA events around every launch in a second pass of the same K steps
-           (event pairs between back-to-back launches would perturb `value`).
-`cpu_baseline`: the reference's own six cv2 calls (oracle/cv2_chain.py) on this box's host cores.
-`--impl reference` prints the same line for that CPU implementation alone.
+`value`      frames/s with inputs and outputs resident in HBM (CUDA events over exactly K steps, max over ranks).
+`sustained`  the same loop repeated for >= 1 s (the K-step region is only ~19 ms at K = 20), clocks sampled over it.
+`e2e`        same metric through the public plugin API (PreprocessPipeline.process_batch) from pinned host buffers,
+             H2D and D2H of full frames inside the timed region.
+`e2e_tensor` BASELINE configs[4] leg: pinned frames in, chain fused with the letterbox, only the (B,3,640,640) fp16
+             detector tensor comes back (process_batch_to_tensor); `e2e_keep`: results stay on the GPU (no D2H).
+`streams`    BASELINE configs[3] leg: one paced 1080p@30 camera stream per GPU (capture -> pinned ring -> chain ->
+             pinned result), sustained fps and capture->result latency percentiles.
+`roofline`   the dominant kernel (k_chain) against the measured HBM copy bandwidth; its time is measured live with CUDA
+             events around every launch in a second pass of the same K steps; DRAM traffic and instruction counts come
+             from the committed ncu capture profiles/final_k_chain.json, whose source hash must match the tree.
+`cpu_baseline` / `--impl reference`: the reference's OWN PreprocessPipeline (oracle/_ref, installed by build()) on all
+             host cores, one loop for both (64 frames per step, frame-parallel, one cv2 thread per process).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -31,10 +37,16 @@ if ROOT not in sys.path:
 
 H, W, BATCH = 1080, 1920, 64
 SPACE, CLIP, GRID, KSIZE = "YCrCb", 2.0, 8, 5
-POOL = 8                                   # distinct synthetic frames, tiled to the batch
+POOL = 8                                   # distinct frames, tiled to the batch
 FRAME_BYTES = 3 * H * W
 ALGO_BYTES_PER_FRAME = 2 * FRAME_BYTES     # read BGR once + write BGR once
+TENSOR_SIZE = 640
+TENSOR_BYTES = 3 * TENSOR_SIZE * TENSOR_SIZE * 2
 METRIC, UNIT = "1080p preproc-chain frames/s", "frames/s"
+CHAIN_CFG = {"enabled": True, "chain": [
+    {"name": "CLAHEDehaze", "params": {"space": SPACE, "clip_limit": CLIP, "tile_grid": GRID}},
+    {"name": "MedianDerain", "params": {"ksize": KSIZE}}]}
+REF_ROOT = os.path.join(ROOT, "oracle", "_ref", "road-vision-system")
 
 
 # ----------------------------------------------------------------------------- sharding / reductions
@@ -58,6 +70,11 @@ def _reduce(x, op, use_cuda):
 def max_over_ranks(x, use_cuda=True):
     import torch.distributed as dist
     return _reduce(x, dist.ReduceOp.MAX, use_cuda)
+
+
+def min_over_ranks(x, use_cuda=True):
+    import torch.distributed as dist
+    return _reduce(x, dist.ReduceOp.MIN, use_cuda)
 
 
 def sum_over_ranks(x, use_cuda=True):
@@ -115,56 +132,114 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ----------------------------------------------------------------------------- CPU arm (reference's cv2 calls)
-_WORKER_FRAMES = None
+# ----------------------------------------------------------------------------- frame pool
+def load_pool():
+    """The committed pool of reference-fogged 1080p frames (tests/golden/make_bench_pool.py), SHA-1 checked."""
+    import cv2
+    import numpy as np
+    d = os.path.join(ROOT, "tests", "golden", "pool_1080p")
+    frames = []
+    for line in open(os.path.join(d, "index.txt")):
+        if line.startswith("#") or not line.strip():
+            continue
+        name, _level, _seed, sha, _ref_sha = line.strip().split("|")[:5]
+        img = cv2.imdecode(np.fromfile(os.path.join(d, name), np.uint8), cv2.IMREAD_COLOR)
+        if img is None or img.shape != (H, W, 3) or hashlib.sha1(img.tobytes()).hexdigest() != sha:
+            raise SystemExit(f"bench: {name} does not decode to the recorded frame")
+        frames.append(img)
+    if len(frames) != POOL:
+        raise SystemExit("bench: frame pool incomplete")
+    return np.stack(frames)
 
 
-def _cpu_init(frames):
-    """Pool initializer: every spawned worker receives the frame pool once, outside any timed region."""
-    global _WORKER_FRAMES
+def pool_reference_shas():
+    d = os.path.join(ROOT, "tests", "golden", "pool_1080p")
+    return [ln.strip().split("|")[4] for ln in open(os.path.join(d, "index.txt")) if ln.strip() and not ln.startswith("#")]
+
+
+DATA = ("synthetic: 8 distinct 1080p road scenes fogged by the reference's EnhancedFogSynthesizer (src/augment/fog.py, "
+        "tools/fog_batch.py:19-27 parameters, seeded) + rain streaks, tiled to the batch (tests/golden/pool_1080p)")
+
+
+# ----------------------------------------------------------------------------- CPU arm: the reference's own classes
+_W = {}
+
+
+def _cpu_init(frames, ref_root):
+    """Pool initializer (spawned, never forked: a forked child inherits cv2's thread-pool state and can deadlock): every
+    worker gets the frame pool once and builds the pipeline it will time, outside any timed region."""
     import cv2
     cv2.setNumThreads(1)
-    _WORKER_FRAMES = frames
+    _W["frames"] = frames
+    _W["pipe"], _W["kind"] = _make_cpu_pipeline(ref_root)
 
 
-def _cpu_worker(args):
-    """Runs in a *spawned* worker (never forked: a forked child inherits cv2's thread-pool state and can deadlock)."""
+def _make_cpu_pipeline(ref_root):
+    """The reference's PreprocessPipeline from oracle/_ref when build() installed it (kind "reference"), else the restated
+    six cv2 calls of oracle/cv2_chain.py (kind "port"; proven equal by tests/test_reference_equivalence.py)."""
+    if ref_root and os.path.isfile(os.path.join(ref_root, "src", "preprocess", "pipeline.py")):
+        saved = {k: sys.modules.pop(k) for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]}
+        sys.path.insert(0, ref_root)
+        try:
+            from src.preprocess import PreprocessPipeline as RefPipeline      # the reference, unmodified
+            pipe = RefPipeline(CHAIN_CFG)
+        finally:
+            sys.path.remove(ref_root)
+            for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+                del sys.modules[k]
+            sys.modules.update(saved)
+        return pipe, "reference"
     from oracle import cv2_chain
-    idx, reps = args
+    return (lambda img, ts=None: cv2_chain.chain(img, SPACE, CLIP, GRID, KSIZE)), "port"
+
+
+def _cpu_worker(idx):
     t0 = time.perf_counter()
-    for _ in range(reps):
-        for i in idx:
-            cv2_chain.chain(_WORKER_FRAMES[i % len(_WORKER_FRAMES)], SPACE, CLIP, GRID, KSIZE)
-    return time.perf_counter() - t0
+    fr = _W["frames"]
+    for i in idx:
+        _W["pipe"](fr[i % len(fr)])
+    return time.perf_counter() - t0, _W["kind"]
 
 
-def cpu_chain_fps(frames, budget_s, mode):
-    """frames/s of the reference's cv2 chain on the host. mode 'threads': cv2's own pool (as shipped);
-    mode 'procs': one single-threaded cv2 per core, frame-parallel (highest CPU throughput)."""
-    import cv2
-    from oracle import cv2_chain
-    if mode == "threads":
-        cv2_chain.chain(frames[0], SPACE, CLIP, GRID, KSIZE)
-        n, t0 = 0, time.perf_counter()
-        while True:
-            for f in frames:
-                cv2_chain.chain(f, SPACE, CLIP, GRID, KSIZE)
-            n += len(frames)
-            if time.perf_counter() - t0 > budget_s:
-                break
-        return n / (time.perf_counter() - t0), cv2.getNumThreads(), n
+def cpu_reference(pool, steps, warmup, budget_s=None):
+    """ONE loop for `--impl reference` and for the `cpu_baseline` leg: every step is the whole 64-frame batch of the
+    configured workload, frame-parallel over all host cores (one single-threaded cv2 per process), a barrier per step.
+    steps: number of timed steps; with budget_s, as many steps as fit in that many seconds (at least 3)."""
     import multiprocessing as mp
+    import cv2
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    per = 2
-    reps = max(1, int(budget_s / (0.04 * per)))          # ~40 ms per 1080p frame on one core
-    reps = min(reps, 8)
-    with mp.get_context("spawn").Pool(cores, initializer=_cpu_init, initargs=(list(frames),)) as pool:
-        pool.map(_cpu_worker, [([0], 1)] * cores)                 # warm the workers
-        t0 = time.perf_counter()
-        pool.map(_cpu_worker, [(list(range(c, c + per)), reps) for c in range(cores)])
+    chunks = [list(range(c, BATCH, cores)) for c in range(cores)]
+    chunks = [c for c in chunks if c]
+    with mp.get_context("spawn").Pool(len(chunks), initializer=_cpu_init, initargs=(list(pool), REF_ROOT)) as pp:
+        kind = "port"
+        for _ in range(max(warmup, 1)):
+            kind = pp.map(_cpu_worker, chunks)[0][1]
+        done, t0 = 0, time.perf_counter()
+        while True:
+            pp.map(_cpu_worker, chunks)
+            done += 1
+            if budget_s is None and done >= steps:
+                break
+            if budget_s is not None and done >= 3 and time.perf_counter() - t0 >= budget_s:
+                break
         dt = time.perf_counter() - t0
-    n = cores * per * reps
-    return n / dt, cores, n
+    fps = BATCH * done / dt
+    # as shipped: one process, cv2's own thread pool (what `python main_preview.py` does); reported, not the baseline
+    pipe, _ = _make_cpu_pipeline(REF_ROOT)
+    cv2.setNumThreads(-1)
+    pipe(pool[0])
+    n, t1 = 0, time.perf_counter()
+    while n < 8 or time.perf_counter() - t1 < 1.5:
+        pipe(pool[n % len(pool)])
+        n += 1
+    fps_shipped = n / (time.perf_counter() - t1)
+    what = ("reference's own PreprocessPipeline (oracle/_ref/road-vision-system/src/preprocess)" if kind == "reference"
+            else "reference's six cv2 calls restated (oracle/cv2_chain.py)")
+    return {"value": fps, "unit": UNIT, "cores": len(chunks), "kind": kind,
+            "sample": f"{done} steps x {BATCH} x 1080p frames ({dt:.1f} s), {what}, cv2 {cv2.__version__}, frame-parallel "
+                      f"{len(chunks)} processes x 1 cv2 thread; as shipped (1 process, {cv2.getNumThreads()} cv2 threads): "
+                      f"{fps_shipped:.1f} fps",
+            "steps": done, "seconds": dt, "as_shipped_fps": fps_shipped}
 
 
 def bind_near_gpu(index):
@@ -189,17 +264,11 @@ def bind_near_gpu(index):
         return f"affinity unchanged ({type(e).__name__})"
 
 
-def make_pool():
-    import rvb200  # noqa: F401  (package import only; no GPU needed for the generator)
-    from rvb200 import synth
-    return synth.frame_pool(H, W, POOL, base_seed=2000)
-
-
 def base_line(n_gpus, steps, warmup):
     return {
         "metric": METRIC, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-        "data": "synthetic (seeded road scenes + fog + rain streaks, 8 distinct 1080p frames tiled to the batch)",
+        "data": DATA,
         "config": {"workload": "BASELINE configs[1]: 1920x1080 batch-64 chain, YCrCb, clip 2.0, tile_grid 8, MedianDerain k5",
                    "frames_per_gpu_per_step": BATCH, "global_batch": BATCH * n_gpus, "parallelism": f"frames sharded x{n_gpus}, no collective",
                    "l2": "per-step inputs+outputs (796 MB per GPU) exceed the 126 MB L2; no explicit flush"},
@@ -207,38 +276,76 @@ def base_line(n_gpus, steps, warmup):
 
 
 def run_reference(args, rank, world):
-    """The reference's CPU implementation of the path (its cv2 calls) on all host cores; rank 0 only."""
+    """The reference's CPU implementation of the path on all host cores; rank 0 only.  Same config and metric as the GPU arm,
+    every step is the full 64-frame batch."""
     if rank != 0:
         return
-    pool = make_pool()
-    import multiprocessing as mp
-    cores = len(os.sched_getaffinity(0))
-    sample = min(max(16, 2 * cores), 4 * BATCH)   # frames per step: two per worker so every host core stays busy
-    frames = [pool[i % POOL] for i in range(sample)]
-    with mp.get_context("spawn").Pool(cores, initializer=_cpu_init, initargs=(list(pool),)) as pp:
-        chunks = [list(range(c, sample, cores)) for c in range(cores)]
-        chunks = [c for c in chunks if c]
-        for _ in range(max(args.warmup, 1)):
-            pp.map(_cpu_worker, [(c, 1) for c in chunks])
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            pp.map(_cpu_worker, [(c, 1) for c in chunks])
-        dt = time.perf_counter() - t0
-    fps_procs = sample * args.steps / dt
-    fps_thr, nthr, _ = cpu_chain_fps(frames[:4], 3.0, "threads")
-    best = max(fps_procs, fps_thr)
+    pool = load_pool()
+    res = cpu_reference(pool, args.steps, args.warmup)
     line = base_line(args.gpus, args.steps, args.warmup)
     line.update({
-        "impl": "reference", "value": best, "ms_per_step": 1e3 * sample / best,
-        "config": dict(line["config"], sample=f"{sample} frames per step (bounded sample of the 64-frame batch)"),
-        "cpu_baseline": {"value": best, "unit": UNIT, "cores": cores if fps_procs >= fps_thr else nthr, "kind": "port",
-                         "sample": f"{sample} x 1080p frames/step; reference's six cv2 calls (oracle/cv2_chain.py, cv2 "
-                                   f"{__import__('cv2').__version__}); frame-parallel {cores} procs x 1 thread = {fps_procs:.1f} fps, "
-                                   f"as shipped ({nthr} cv2 threads) = {fps_thr:.1f} fps"},
-        "e2e": {"value": best, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "value": res["value"], "ms_per_step": 1e3 * BATCH / res["value"],
+        "cpu_baseline": res,
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def timed_loop(fn, steps):
+    """Wall-clock time of `steps` host-synchronous calls, max over ranks, barrier on both sides."""
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = time.perf_counter() - t0
+    return max_over_ranks(dt)
+
+
+def stream_leg(rvb200, local_rank, pool, seconds, fps, skip_s=2.0):
+    """One paced camera stream on this rank's GPU: SyntheticReader (paced) -> BatchFeeder (pinned ring, capture timestamps) ->
+    PreprocessPipeline.process_batch (its own Context) -> pinned result; latency = result ready - capture timestamp."""
+    import numpy as np
+    from rvb200.io_video.capture import SyntheticReader
+    ctx = rvb200.Context(local_rank)
+    pipe = rvb200.PreprocessPipeline(CHAIN_CFG, context=ctx)
+    nframes = int(seconds * fps)
+    vs = rvb200.VideoSource(reader=SyntheticReader(list(pool[:4]), limit=nframes))
+    feeder = rvb200.BatchFeeder(vs, batch=1, shape=(H, W, 3), alloc=ctx.pinned_empty, depth=3, fps=fps)
+    out = ctx.pinned_empty((1, H, W, 3))
+    warm = ctx.pinned_empty((1, H, W, 3))
+    warm[:] = pool[:1]
+    for _ in range(3):                                   # context warm-up (allocations, tables) before the camera starts
+        pipe.process_batch(warm, out=out)
+    lat, stamps = [], []
+    for b in feeder:
+        pipe.process_batch(b.frames, out=out[:b.count])
+        done = time.time()
+        lat.extend(done - b.ts)
+        stamps.extend(b.ts)
+        feeder.release(b)
+    ctx.close()
+    lat, stamps = np.array(lat), np.array(stamps)
+    keep = stamps >= stamps[0] + skip_s
+    lat_k, st_k = np.sort(lat[keep]), stamps[keep]
+    span = float(st_k[-1] - st_k[0]) if len(st_k) > 1 else 0.0
+    return {"frames": int(keep.sum()), "fps": (len(st_k) - 1) / span if span > 0 else 0.0,
+            "p50_ms": 1e3 * float(lat_k[len(lat_k) // 2]), "p99_ms": 1e3 * float(lat_k[min(len(lat_k) - 1, int(len(lat_k) * 0.99))]),
+            "max_ms": 1e3 * float(lat_k[-1])}
+
+
+def load_ncu_constants(rvb200):
+    """DRAM bytes and executed warp instructions of one k_chain launch from the committed ncu capture, tied to the source tree."""
+    path = os.path.join(ROOT, "profiles", "final_k_chain.json")
+    tree = rvb200.kernel_source_hash()
+    try:
+        j = json.load(open(path))
+    except Exception:
+        return None, {"traffic_source": None, "tree_hash": tree, "note": "profiles/final_k_chain.json missing"}
+    info = {"traffic_source": "profiles/final_k_chain.json", "capture_hash": j.get("source_hash"), "tree_hash": tree,
+            "hash_match": j.get("source_hash") == tree, "capture": j.get("capture")}
+    return j, info
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -258,7 +365,7 @@ def run_gpu(args, rank, world, local_rank):
     if args.prefetch >= 0:
         ctx.set_option("prefetch_ctas", args.prefetch)
     params = rvb200.Params.make(SPACE, CLIP, GRID, KSIZE)
-    pool = make_pool()
+    pool = load_pool()
     a, _ = shard_range(BATCH * world, rank, world)            # this rank's slab of the global frame index space
     host = np.stack([pool[(a + i) % POOL] for i in range(BATCH)])
     d_in = torch.from_numpy(host).cuda()
@@ -272,7 +379,14 @@ def run_gpu(args, rank, world, local_rank):
         ctx.submit_device(d_in.data_ptr(), d_out.data_ptr(), BATCH, H, W, params, stream=stream)
 
     step(); torch.cuda.synchronize()
-    gpu_first = d_out[0].cpu().numpy()          # checked against the CPU chain in the cpu_baseline leg below
+    # parity gate: the GPU output of every distinct pool frame must hash to what the REFERENCE's PreprocessPipeline produced
+    # when the pool was generated (tests/golden/pool_1080p/index.txt) -- never report a wrong kernel's speed
+    shas = pool_reference_shas()
+    first = d_out[:POOL].cpu().numpy()
+    for i in range(POOL):
+        if hashlib.sha1(first[i].tobytes()).hexdigest() != shas[(a + i) % POOL]:
+            raise SystemExit(f"bench: CUDA chain output of pool frame {(a + i) % POOL} differs from the reference's; refusing to report")
+    gpu_first = first[0]
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -295,6 +409,21 @@ def run_gpu(args, rank, world, local_rank):
     frames_total = sum_over_ranks(BATCH * args.steps)
     value = frames_total / (ms_max * 1e-3)
 
+    # sustained: the same step, back to back, for at least ~1.2 s of device time (same events, same stream)
+    n_sus = max(args.steps, int(1.3e3 / max(ms / args.steps, 1e-3)))
+    barrier(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n_sus):
+        step()
+    e1.record()
+    torch.cuda.synchronize(); barrier()
+    ms_sus = max_over_ranks(e0.elapsed_time(e1))
+    sustained = {"steps": n_sus, "seconds": ms_sus * 1e-3, "value": sum_over_ranks(BATCH * n_sus) / (ms_sus * 1e-3), "unit": UNIT}
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "the K timed steps + the sustained loop (%d steps), %.2f s" % (n_sus, t1 - t0)
+
     # second pass: per-kernel device time with an event pair around every launch
     ctx.set_option("kernel_timing", 1)
     ctx.kernel_times(reset=True)
@@ -303,36 +432,69 @@ def run_gpu(args, rank, world, local_rank):
     torch.cuda.synchronize()
     kt = ctx.kernel_times(reset=True)
     ctx.set_option("kernel_timing", 0)
-    # keep the same load running until nvidia-smi (100 ms period) has seen it for >= 1.5 s, then read the clocks
-    while time.time() - t0 < 1.5:
-        step()
-        torch.cuda.synchronize()
-    t1 = time.time()
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
-    if clocks is not None:
-        clocks["window"] = "timed steps + per-kernel pass + same-load soak, %.2f s" % (t1 - t0)
 
-    # end to end through the plugin API from pinned host memory
-    pin_in, pin_out = ctx.pinned_empty(host.shape), ctx.pinned_empty(host.shape)
-    pin_in[:] = host
-    pl = rvb200.PreprocessPipeline({"enabled": True, "device": local_rank, "chain": [
-        {"name": "CLAHEDehaze", "params": {"space": SPACE, "clip_limit": CLIP, "tile_grid": GRID}},
-        {"name": "MedianDerain", "params": {"ksize": KSIZE}}]})
-    e2e_steps = max(3, min(args.steps, 10))
-    if args.no_e2e:
-        e2e_steps = 0
-    for _ in range(2 if e2e_steps else 0):
-        pl.process_batch(pin_in, out=pin_out)
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        pl.process_batch(pin_in, out=pin_out)
-        _ = int(pin_out[-1, -1, -1, 0])                       # host read of the step's result
-    w1 = time.perf_counter()
-    if e2e_steps and not np.array_equal(pin_out[0], gpu_first):
-        raise SystemExit("bench: end-to-end output differs from the device-resident output")
-    e2e_s = max_over_ranks(w1 - w0)
-    e2e_value = sum_over_ranks(BATCH * e2e_steps) / e2e_s if e2e_steps else None
+    # ---- end to end through the plugin API from pinned host memory
+    pl = rvb200.PreprocessPipeline(dict(CHAIN_CFG, device=local_rank), context=ctx)
+    e2e = e2e_tensor = e2e_keep = None
+    if not args.no_e2e:
+        pin_in, pin_out = ctx.pinned_empty(host.shape), ctx.pinned_empty(host.shape)
+        pin_in[:] = host
+        e2e_steps = max(3, min(args.steps, 10))
+
+        def full():
+            pl.process_batch(pin_in, out=pin_out)
+            return int(pin_out[-1, -1, -1, 0])                    # host read of the step's result
+
+        for _ in range(2):
+            full()
+        e2e_s = timed_loop(full, e2e_steps)
+        if not np.array_equal(pin_out[0], gpu_first):
+            raise SystemExit("bench: end-to-end output differs from the device-resident output")
+        e2e = {"value": sum_over_ranks(BATCH * e2e_steps) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": BATCH * FRAME_BYTES,
+               "d2h_bytes_per_step": BATCH * FRAME_BYTES, "steps": e2e_steps,
+               "api": "PreprocessPipeline.process_batch(pinned in, pinned out)"}
+
+        # configs[4]: chain fused with the letterbox, only the detector tensor returns
+        pin_t = ctx.pinned_empty((BATCH, 3, TENSOR_SIZE, TENSOR_SIZE), np.float16)
+
+        def tens():
+            pl.process_batch_to_tensor(pin_in, size=TENSOR_SIZE, out=pin_t)
+            return float(pin_t[-1, -1, -1, -1])
+
+        for _ in range(2):
+            tens()
+        t_s = timed_loop(tens, e2e_steps)
+        want_t, _ = pl.process_batch_to_tensor(host[:1], size=TENSOR_SIZE)
+        if not np.array_equal(pin_t[0].view(np.uint16), want_t[0].view(np.uint16)):
+            raise SystemExit("bench: pipelined tensor differs from the unpipelined one")
+        e2e_tensor = {"value": sum_over_ranks(BATCH * e2e_steps) / t_s, "unit": UNIT, "h2d_bytes_per_step": BATCH * FRAME_BYTES,
+                      "d2h_bytes_per_step": BATCH * TENSOR_BYTES, "steps": e2e_steps,
+                      "workload": "BASELINE configs[4]-style: headline chain fused with letterbox 640 + RGB fp16 NCHW; 64 frames per GPU per step",
+                      "api": "PreprocessPipeline.process_batch_to_tensor(pinned frames, out=pinned (B,3,640,640) float16)"}
+
+        def keep():
+            dev, _ = pl.process_batch_to_tensor(pin_in, size=TENSOR_SIZE, out="device")
+            return dev
+
+        for _ in range(2):
+            keep()
+        k_s = timed_loop(keep, e2e_steps)
+        e2e_keep = {"value": sum_over_ranks(BATCH * e2e_steps) / k_s, "unit": UNIT, "h2d_bytes_per_step": BATCH * FRAME_BYTES,
+                    "d2h_bytes_per_step": 0, "steps": e2e_steps,
+                    "api": "PreprocessPipeline.process_batch_to_tensor(pinned frames, out='device'): the tensor stays on the GPU for the detector"}
+        del pin_in, pin_out, pin_t
+
+    # ---- configs[3]: one paced 1080p@30 stream per GPU
+    streams = None
+    if args.stream_seconds > 0:
+        barrier()
+        s = stream_leg(rvb200, local_rank, pool, args.stream_seconds, 30.0)
+        streams = {"streams": world, "per_gpu": 1, "fps_requested": 30.0, "seconds": args.stream_seconds, "excluded_first_s": 2.0,
+                   "fps_min": min_over_ranks(s["fps"]), "fps_mean": sum_over_ranks(s["fps"]) / world,
+                   "latency_ms_p50_max_over_gpus": max_over_ranks(s["p50_ms"]), "latency_ms_p99_max_over_gpus": max_over_ranks(s["p99_ms"]),
+                   "latency_ms_max": max_over_ranks(s["max_ms"]), "frames": sum_over_ranks(s["frames"]),
+                   "path": "SyntheticReader paced at 30 fps -> BatchFeeder (pinned ring, time.time() at capture) -> "
+                           "PreprocessPipeline(context=own Context).process_batch -> pinned result; latency = result - capture"}
 
     if rank != 0:
         return
@@ -347,12 +509,15 @@ def run_gpu(args, rank, world, local_rank):
     avg_launch_s = chain_ms * 1e-3 / max(chain_n, 1)
     achieved = ALGO_BYTES_PER_FRAME * frames_per_launch / avg_launch_s / 1e9 if chain_n else None
     total_k = sum(v[0] for v in kt.values())
+    ncu, ncu_info = load_ncu_constants(rvb200)
+    per64 = frames_per_launch / 64.0
     line = base_line(world, args.steps, args.warmup)
     line.update({
         "value": value, "ms_per_step": ms_max / args.steps, "gpu_launches": launches, "clocks": clocks,
-        "host_affinity": numa,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * FRAME_BYTES, "d2h_bytes_per_step": BATCH * FRAME_BYTES,
-                "steps": e2e_steps, "api": "PreprocessPipeline.process_batch(pinned in, pinned out)"},
+        "sustained": sustained, "host_affinity": numa,
+        "parity": "all 8 pool frames: SHA-1 of the CUDA output equals the SHA-1 of the reference PreprocessPipeline output recorded "
+                  "with the pool (tests/golden/pool_1080p/index.txt)",
+        "e2e": e2e, "e2e_tensor": e2e_tensor, "e2e_keep": e2e_keep, "streams": streams,
         "roofline": {"bound": "hbm", "kernel": "k_chain<YCrCb,5>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME, "frames_per_launch": frames_per_launch,
@@ -360,56 +525,40 @@ def run_gpu(args, rank, world, local_rank):
                      "kernel_share_of_step": {k: (v[0] / total_k if total_k else None) for k, v in kt.items()},
                      "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kt.items()},
                      "whole_chain_achieved_gbs": ALGO_BYTES_PER_FRAME * value / world / 1e9,
-                     "traffic": TRAFFIC_NCU},
+                     "traffic": (ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) * per64 if ncu else None,
+                     "traffic_info": ncu_info},
     })
     # why the HBM fraction is low: k_chain is bound by instruction issue, not by memory.  Warp instructions
-    # per launch come from the committed ncu capture, the launch time is the live measurement above.
-    sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
-    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
-    issue_peak = sms * 4 * sm_clock * 1e6                      # one warp instruction per scheduler per clock
-    line["roofline"]["issue"] = {
-        "warp_instr_per_launch": WARP_INSTR_NCU * frames_per_launch / 64.0, "thread_instr_per_pixel": WARP_INSTR_NCU * 32 / (64.0 * H * W),
-        "achieved_gwarp_instr_s": WARP_INSTR_NCU * frames_per_launch / 64.0 / avg_launch_s / 1e9 if chain_n else None,
-        "peak_gwarp_instr_s": issue_peak / 1e9,
-        "frac": (WARP_INSTR_NCU * frames_per_launch / 64.0 / avg_launch_s / issue_peak) if chain_n else None,
-        "source": "smsp__inst_executed.sum of one k_chain launch (profiles/r1_v9_k_chain_summary.txt); peak = SMs x 4 schedulers x SM clock"}
+    # per launch come from the committed ncu capture (hash-tied to the tree), the launch time is the live measurement above.
+    if ncu and chain_n:
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        issue_peak = sms * 4 * sm_clock * 1e6                      # one warp instruction per scheduler per clock
+        wi = ncu["warp_instructions"] * per64
+        line["roofline"]["issue"] = {
+            "warp_instr_per_launch": wi, "thread_instr_per_pixel": ncu["warp_instructions"] * 32 / (64.0 * H * W),
+            "achieved_gwarp_instr_s": wi / avg_launch_s / 1e9, "peak_gwarp_instr_s": issue_peak / 1e9,
+            "frac": wi / avg_launch_s / issue_peak,
+            "source": "smsp__inst_executed.sum of one 64-frame k_chain launch (profiles/final_k_chain.json); peak = SMs x 4 schedulers x SM clock"}
     if world == 1 and not args.no_cpu:
-        fps_p, cores_p, n_p = cpu_chain_fps(list(pool), 6.0, "procs")
-        from oracle import cv2_chain            # the CPU leg doubles as the checker: never report a wrong kernel's speed
-        if not np.array_equal(gpu_first, cv2_chain.chain(host[0], SPACE, CLIP, GRID, KSIZE)):
-            raise SystemExit("bench: CUDA chain differs from the reference's cv2 chain; refusing to report")
-        line["parity"] = "frame 0 of the timed batch bit-exact vs the reference's cv2 chain"
-        fps_t, cores_t, n_t = cpu_chain_fps(list(pool[:4]), 4.0, "threads")
-        import cv2
-        best = max(fps_p, fps_t)
-        line["cpu_baseline"] = {
-            "value": best, "unit": UNIT, "cores": cores_p if fps_p >= fps_t else cores_t, "kind": "port",
-            "sample": f"reference's six cv2 calls (oracle/cv2_chain.py, cv2 {cv2.__version__}) on the same 1080p frames: "
-                      f"frame-parallel {cores_p} procs x 1 thread, {n_p} frames = {fps_p:.1f} fps; "
-                      f"as shipped ({cores_t} cv2 threads), {n_t} frames = {fps_t:.1f} fps"}
+        line["cpu_baseline"] = cpu_reference(pool, 0, 1, budget_s=args.cpu_seconds)
     print(json.dumps(line), flush=True)
-
-
-# DRAM bytes of one k_chain launch (64 x 1080p frames: dram__bytes_read.sum 403.5 MB + dram__bytes_write.sum 356.1 MB) and its
-# executed warp instructions, from the committed `ncu --set full` capture profiles/r1_v9_k_chain_summary.txt; algorithmic
-# bytes of that launch: 796.3 MB.  (The shipped 5x5 network has since lost 8 of its 748 operations: the instruction count is
-# about 1 % lower than this capture, the traffic is unchanged.)
-TRAFFIC_NCU = 759.6e6
-WARP_INSTR_NCU = 782662144
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=1200, help="timed steps (default sized so that the timed region spans > 1 s)")
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--group", type=int, default=0, help="frames per hist->lut->chain group (0 = library default)")
     ap.add_argument("--chunk", type=int, default=0, help="frames per host pipeline chunk (0 = library default)")
     ap.add_argument("--overlap", type=int, default=-1, help="groups per batch for the histogram/chain overlap (-1 = library default)")
     ap.add_argument("--prefetch", type=int, default=-1, help="k_chain L2 prefetch distance in CTAs per SM (-1 = library default, 0 = off)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end legs (profiling runs)")
+    ap.add_argument("--stream-seconds", type=float, default=32.0, help="length of the paced-stream leg (0 = skip)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="time budget of the cpu_baseline leg")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -422,6 +571,8 @@ def main():
         raise SystemExit(subprocess.call(cmd))
 
     if args.impl == "reference":
+        if args.steps > 200:
+            args.steps = 20                     # the CPU arm's default: 20 x 64 frames (a few seconds)
         run_reference(args, rank, world)
         return
     if world > 1:

@@ -17,10 +17,16 @@
  *   rv_gray_span       PreprocessPipeline._low_contrast       pipeline.py:24-30
  *   rv_submit/rv_wait  (new) batched multi-frame entry fed from pinned host buffers; no reference
  *                      counterpart (the reference loop is one frame in flight, main_preview.py:88-142)
+ *   rv_submit_io       (new) the same with every end of the job placed independently: what src/io_video/capture.py:18-21
+ *                      captured on the host goes in, the processed frames and / or the detector's input tensor
+ *                      (main_preview.py:99 -> src/detect/yolo_ultralytics.py:28-35) come out on the host or stay on the GPU
  *
  * Conventions: plain C types only; every function returns 0 on success or a negative rv_status;
  * rv_last_error(ctx) gives the message.  A context is bound to one CUDA device, owns its streams and
- * workspaces, and is not thread-safe; different contexts may be used from different threads.
+ * workspaces, and is not thread-safe: one host thread at a time may call into a context; different contexts may be used
+ * from different threads.  Within that thread, work may be enqueued on several caller streams (`stream` arguments): every use of
+ * a context workspace is ordered after the previous one with CUDA events, so submissions on different streams serialise on the
+ * GPU where they share a workspace instead of racing (use one context per stream for concurrency).
  * There is NO CPU fallback: without a usable sm_100 device rv_create fails.
  *
  * Frames are uint8 BGR, interleaved, `h` rows of `w` pixels, `pitch` bytes between rows
@@ -117,6 +123,29 @@ int rv_chain_u8(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int 
 int rv_submit(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w,
               size_t in_pitch, size_t out_pitch, const rv_params *p, int mem_kind, void *stream);
 int rv_wait(rv_ctx *ctx);
+
+/* General asynchronous job (host memory goes through the context's chunked H2D / kernels / D2H pipeline streams; rv_wait
+ * blocks until it is finished).  Every end has its own rv_mem kind:
+ *   in        frames, host (pageable or pinned) or device
+ *   out       processed full-resolution frames, host or device; NULL = not wanted (only legal with `tensor`)
+ *   tensor    detector input as rv_chain_letterbox_f16 produces it (n*3*S*S halves), host or device; NULL = none
+ *   processed optional host array of n ints (gate decisions, as rv_chain_u8)
+ * A device `in` must be complete before the call (the pipeline streams do not wait for other streams); device outputs are
+ * complete after rv_wait.  Results that stay on the GPU never cross PCIe: pinned frames in, device frames / tensor out is
+ * the path for a detector on the same GPU (main_preview.py:94,99). */
+typedef struct rv_io {
+    const uint8_t *in;
+    size_t in_pitch;
+    uint8_t *out;
+    size_t out_pitch;
+    uint16_t *tensor;
+    int32_t *processed;
+    int32_t in_kind, out_kind, tensor_kind;
+    int32_t tensor_size;    /* S of the S x S letterbox */
+    int32_t pad_value;      /* 114 in ultralytics */
+    int32_t reserved;
+} rv_io;
+int rv_submit_io(rv_ctx *ctx, const rv_io *io, int n, int h, int w, const rv_params *p);
 
 /* Stage-level entry points (parity tests). All synchronous; mem_kind applies to every pointer. */
 /* hist: n*grid*grid*256 int32; luma (optional): n*h*w bytes, packed; span (optional): n*2 int32 {min,max} of gray */

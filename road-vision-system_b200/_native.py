@@ -33,6 +33,39 @@ class Params(C.Structure):
                    float(clip_limit), 1 if gate else 0, 0, float(gate_thresh))
 
 
+class IO(C.Structure):
+    """rv_io: one job of rv_submit_io -- every end (frames in, frames out, detector tensor out) has its own memory kind."""
+    _fields_ = [
+        ("in_", C.c_void_p), ("in_pitch", C.c_size_t), ("out", C.c_void_p), ("out_pitch", C.c_size_t),
+        ("tensor", C.c_void_p), ("processed", C.c_void_p),
+        ("in_kind", C.c_int32), ("out_kind", C.c_int32), ("tensor_kind", C.c_int32),
+        ("tensor_size", C.c_int32), ("pad_value", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class DeviceArray:
+    """A result that stayed on the GPU (process_batch(..., out="device")): device memory owned by the context, freed when
+    this object is garbage-collected.  Exposes `__cuda_array_interface__` (version 3), so `torch.as_tensor(x, device="cuda")`
+    and `cupy.asarray(x)` wrap it without a copy; `numpy()` downloads it."""
+
+    def __init__(self, ctx, shape, dtype=np.uint8):
+        self.shape, self.dtype = tuple(int(v) for v in shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        ctx._ck(ctx._lib.rv_alloc_device(ctx._h, max(self.nbytes, 1), C.byref(p)))
+        self.ptr, self.ctx = p.value, ctx
+        self._finalizer = weakref.finalize(self, ctx._lib.rv_free_device, ctx._h, C.c_void_p(p.value))
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": self.dtype.str, "data": (self.ptr, False), "version": 3, "strides": None}
+
+    def numpy(self):
+        out = np.empty(self.shape, self.dtype)
+        self.ctx._ck(self.ctx._lib.rv_memcpy(self.ctx._h, out.ctypes.data, C.c_void_p(self.ptr), self.nbytes, 1))
+        return out
+
+
 def library_path():
     return _SO
 
@@ -47,6 +80,21 @@ def build_library(force=False, verbose=False):
         cmd = ["make", "-C", _CSRC, "librv_b200.so"] + (["-B"] if force else [])
         subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
     return _SO
+
+
+KERNEL_SOURCES = ("Makefile", "rv_common.cuh", "rv_colour.cuh", "rv_hist_lut.cuh", "rv_chain.cuh", "rv_median_net.h", "rv_lab_tables.h")
+
+
+def kernel_source_hash():
+    """SHA-256 (first 16 hex digits) over the files that determine the device code of the chain's kernels (not the host-side
+    C ABI).  profiles/final_*.json records it with every ncu capture; bench.py and the CPU test suite compare it with the tree,
+    so profile-derived constants can never silently outlive the code they were measured on."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(_CSRC, name), "rb") as fh:
+            h.update(name.encode() + b"\0" + fh.read() + b"\0")
+    return h.hexdigest()[:16]
 
 
 _lib = None
@@ -75,6 +123,7 @@ EXPORTS = {
                               C.POINTER(Params), C.c_int, _i32p, C.c_void_p]),
     "rv_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t,
                             C.POINTER(Params), C.c_int, C.c_void_p]),
+    "rv_submit_io": (C.c_int, [C.c_void_p, C.POINTER(IO), C.c_int, C.c_int, C.c_int, C.POINTER(Params)]),
     "rv_kernel_time": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]),
     "rv_kernel_time_reset": (C.c_int, [C.c_void_p]),
     "rv_wait": (C.c_int, [C.c_void_p]),
@@ -260,6 +309,41 @@ class Context:
     def wait(self):
         self._ck(self._lib.rv_wait(self._h))
 
+    def _end(self, x):
+        """(pointer, rv_mem kind) of one end of a job: numpy array (pinned or pageable), DeviceArray, or a raw device pointer."""
+        if x is None:
+            return None, MEM_HOST
+        if isinstance(x, np.ndarray):
+            if not x.flags.c_contiguous:
+                raise ValueError("arrays handed to submit_io must be C-contiguous")
+            return x.ctypes.data, self.mem_kind(x)
+        if isinstance(x, DeviceArray):
+            return x.ptr, MEM_DEVICE
+        if hasattr(x, "__cuda_array_interface__"):
+            return int(x.__cuda_array_interface__["data"][0]), MEM_DEVICE
+        return int(x), MEM_DEVICE
+
+    def submit_io(self, frames, params, shape=None, out=None, tensor=None, size=640, pad_value=114, processed=None):
+        """rv_submit_io: asynchronous job whose ends live independently on the host or on the GPU; call wait() afterwards.
+
+        frames: (N,H,W,3) uint8 numpy array (pinned or pageable) or a device object / pointer (then pass shape=(N,H,W)).
+        out:    frames result, numpy or device (DeviceArray / anything with __cuda_array_interface__ / int pointer), or None.
+        tensor: (N,3,size,size) float16 detector input, numpy or device, or None."""
+        if isinstance(frames, np.ndarray):
+            _check_frames(frames)
+            n, h, w, _ = frames.shape
+        else:
+            n, h, w = shape
+        io = IO()
+        io.in_, io.in_kind = self._end(frames)
+        io.in_pitch = 3 * w
+        io.out, io.out_kind = self._end(out)
+        io.out_pitch = 3 * w
+        io.tensor, io.tensor_kind = self._end(tensor)
+        io.tensor_size, io.pad_value = int(size), int(pad_value)
+        io.processed = processed.ctypes.data if processed is not None else None
+        self._ck(self._lib.rv_submit_io(self._h, C.byref(io), n, h, w, C.byref(params)))
+
     # -- stage-level entry points (parity tests) ---------------------------------------------
     def luma_hist(self, frames, space, grid, want_luma=True, want_gray=False):
         _check_frames(frames)
@@ -324,8 +408,11 @@ class Context:
         n, h, w, _ = frames.shape
         if out is None:
             out = np.empty((n, 3, size, size), np.float16)
-        full = np.empty_like(frames) if want_full else None
-        kind = MEM_PINNED if (self.mem_kind(frames) == MEM_PINNED and self.mem_kind(out) == MEM_PINNED and not want_full) else MEM_HOST
+        full = None
+        if want_full:
+            full = self._pooled_pinned(frames.shape) if frames.nbytes <= (64 << 20) else np.empty_like(frames)
+        kind = MEM_PINNED if (self.mem_kind(frames) == MEM_PINNED and self.mem_kind(out) == MEM_PINNED and
+                              (full is None or self.mem_kind(full) == MEM_PINNED)) else MEM_HOST
         self._ck(self._lib.rv_chain_letterbox_f16(self._h, frames.ctypes.data, n, h, w, 3 * w, C.byref(params), out.ctypes.data,
                                                   size, pad_value, full.ctypes.data if want_full else None, 3 * w, kind, None))
         return out, full

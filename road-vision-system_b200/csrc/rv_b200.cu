@@ -36,6 +36,32 @@ struct TimedLaunch {
     int which;                              // 0 k_luma_hist, 1 k_build_lut, 2 k_chain
 };
 
+// Ordering of a workspace set between streams: the event is recorded after the last kernel that touches the set; the next
+// user on a different stream waits for it first (two batches submitted on different caller streams never overlap on a set).
+struct WsSync {
+    cudaEvent_t ev = nullptr;
+    cudaStream_t last = nullptr;
+    bool used = false;
+};
+
+// Read-only device tables that depend on the frame geometry only; built once per geometry, uploaded on the stream that
+// first needs them from a page-locked host copy that lives as long as the entry, never rewritten afterwards.
+struct ColTab {                             // k_chain column records for (W, tile width)
+    int w = 0, tw = 0;
+    float *dev = nullptr, *host = nullptr;
+    cudaEvent_t ready = nullptr;
+    cudaStream_t up = nullptr;
+};
+struct LbTab {                              // cv2.resize tables of k_letterbox for (h, w) -> (nh, nw)
+    int h = 0, w = 0, nh = 0, nw = 0;
+    uint8_t *dev = nullptr, *host = nullptr;
+    size_t o_yofs = 0, o_xa = 0, o_ya = 0;
+    cudaEvent_t ready = nullptr;
+    cudaStream_t up = nullptr;
+};
+constexpr int MAX_TABS = 32;                // geometries cached per context before the cache is flushed
+constexpr int MAX_FRAMES_PER_LAUNCH = 32768; // frames ride on gridDim.z / gridDim.y (limit 65535)
+
 }  // namespace
 
 struct rv_ctx {
@@ -45,14 +71,16 @@ struct rv_ctx {
     cudaStream_t pipe[NPIPE] = {};          // H2D / compute / D2H pipeline for host buffers
     Buf hist[NPIPE + 2], quads[NPIPE + 2], lut[NPIPE + 2], flags[NPIPE + 2], mm[NPIPE + 2];   // [NPIPE], [NPIPE+1]: device path
     Buf din[NPIPE + 2], dout[NPIPE + 2];
+    Buf dlb[NPIPE];                         // detector tensors of the host pipeline's chunks
+    WsSync wsync[NPIPE + 2];
+    std::vector<ColTab> coltabs;
+    std::vector<LbTab> lbtabs;
     cudaStream_t aux = nullptr;             // high-priority stream: histogram/LUT of the next group under the current k_chain
     cudaEvent_t ev_entry = nullptr, ev_pre[2] = {}, ev_chain[2] = {};
     long overlap_groups = 0;                // device path: split a batch into this many groups (0/1 = no overlap); measured
                                             // slower on B200 (k_chain leaves no SM resources for co-resident CTAs), kept as an option
     Buf scratch;                            // stage-level calls
-    Buf lbtab, lbfull;                      // letterbox tables / full-resolution intermediate
-    Buf colp;                               // per-column interpolation records of k_chain
-    int colp_w = -1, colp_tw = -1;
+    Buf lbfull;                             // full-resolution intermediate of the unfused letterbox (device path, set NPIPE)
     long launches = 0;
     long group_frames = 0, chunk_frames = 0;
     long prefetch_ctas_per_sm = 0;          // L2 prefetch distance of k_chain in CTAs per SM, option "prefetch_ctas" (0 = off, the
@@ -194,7 +222,24 @@ int check_frames(rv_ctx *ctx, const void *in, const void *out, int n, int h, int
     if (n < 0 || h < 1 || w < 1) return fail(ctx, RV_ERR_ARG, "bad frame shape n=%d h=%d w=%d", n, h, w);
     if (h > 32768 || w > 32768) return fail(ctx, RV_ERR_ARG, "frame too large (%dx%d)", w, h);
     if (ipitch < (size_t)3 * w || opitch < (size_t)3 * w) return fail(ctx, RV_ERR_ARG, "pitch smaller than 3*w");
+    if (in != out && n > 0) {
+        // unified addressing: host and device ranges never coincide, so a numeric overlap is a real one.  Tiles read their
+        // neighbours' halo, so partially overlapping buffers would race exactly like in-place operation.
+        const uintptr_t a0 = (uintptr_t)in, a1 = a0 + (size_t)n * h * ipitch, b0 = (uintptr_t)out, b1 = b0 + (size_t)n * h * opitch;
+        if (a0 < b1 && b0 < a1) return fail(ctx, RV_ERR_ARG, "input and output ranges overlap");
+    }
     return RV_OK;
+}
+
+// pipeline.py:24-30 compares an integer span with a Python float: span < t  <=>  span < ceil(t) for integer spans.  The
+// decision is taken in integers on the device so that it can never differ from the per-frame path at the boundary.
+int gate_thresh_int(double t)
+{
+    if (!(t == t)) return -1;                               // NaN: every comparison is false, nothing is processed
+    const double c = ceil(t);
+    if (c > 1024.0) return 1024;
+    if (c < -1.0) return -1;
+    return (int)c;
 }
 
 int check_params(rv_ctx *ctx, const rv_params *p)
@@ -269,15 +314,32 @@ int launch_chain_t(rv_ctx *ctx, const ChainArgs &a0, int n, cudaStream_t st)
     return RV_OK;
 }
 
+// frames ride on gridDim.z: very large batches of small frames go out in several launches
+template <int MODE, int K>
+int launch_chain_groups(rv_ctx *ctx, const ChainArgs &a0, int n, cudaStream_t st)
+{
+    if (n <= MAX_FRAMES_PER_LAUNCH) return launch_chain_t<MODE, K>(ctx, a0, n, st);
+    for (int f0 = 0; f0 < n; f0 += MAX_FRAMES_PER_LAUNCH) {
+        ChainArgs a = a0;
+        a.src += (size_t)f0 * a.sfstride;
+        a.dst += (size_t)f0 * a.dfstride;
+        if (a.quads) a.quads += (size_t)f0 * (a.g.grid + 1) * (a.g.grid + 1) * 256;
+        if (a.flags) a.flags += f0;
+        if (a.lb_out) a.lb_out += (size_t)f0 * 3 * a.lb_S * a.lb_S;
+        RV_TRY((launch_chain_t<MODE, K>(ctx, a, std::min(MAX_FRAMES_PER_LAUNCH, n - f0), st)));
+    }
+    return RV_OK;
+}
+
 template <int MODE>
 int launch_chain_k(rv_ctx *ctx, const ChainArgs &a, int n, int k, cudaStream_t st)
 {
     switch (k) {
-        case 0: return launch_chain_t<MODE, 0>(ctx, a, n, st);
-        case 3: return launch_chain_t<MODE, 3>(ctx, a, n, st);
-        case 5: return launch_chain_t<MODE, 5>(ctx, a, n, st);
-        case 7: return launch_chain_t<MODE, 7>(ctx, a, n, st);
-        case 9: return launch_chain_t<MODE, 9>(ctx, a, n, st);
+        case 0: return launch_chain_groups<MODE, 0>(ctx, a, n, st);
+        case 3: return launch_chain_groups<MODE, 3>(ctx, a, n, st);
+        case 5: return launch_chain_groups<MODE, 5>(ctx, a, n, st);
+        case 7: return launch_chain_groups<MODE, 7>(ctx, a, n, st);
+        case 9: return launch_chain_groups<MODE, 9>(ctx, a, n, st);
     }
     return fail(ctx, RV_ERR_ARG, "bad ksize %d", k);
 }
@@ -305,19 +367,25 @@ int launch_hist(rv_ctx *ctx, const uint8_t *src, size_t pitch, size_t fstride, c
     const int rps = (g.th + slices - 1) / slices;
     slices = (g.th + rps - 1) / rps;
     if (slices > 1) CK(cudaMemsetAsync(hist, 0, (size_t)n * tiles * 256 * sizeof(int32_t), st));
-    dim3 grid(slices, tiles, n);
-    {
+    // tiles on gridDim.x (up to 256 x 256 of them), slices on y, frames on z in groups
+    for (int f0 = 0; f0 < n; f0 += MAX_FRAMES_PER_LAUNCH) {
+        const int nf = std::min(MAX_FRAMES_PER_LAUNCH, n - f0);
+        dim3 grid(tiles, slices, nf);
+        const uint8_t *s0 = src + (size_t)f0 * fstride;
+        int32_t *h0 = hist + (size_t)f0 * tiles * 256;
+        uint8_t *l0 = luma ? luma + (size_t)f0 * g.H * g.W : nullptr;
+        int32_t *m0 = mm ? mm + 2 * (size_t)f0 : nullptr;
         ScopedTiming tm(ctx, st, 0);
         const bool extra = luma != nullptr || mm != nullptr;
         if (space == RV_SPACE_LAB) {
-            if (extra) k_luma_hist<1, true><<<grid, HIST_THREADS, 0, st>>>(src, pitch, fstride, g, rps, hist, luma, mm);
-            else k_luma_hist<1, false><<<grid, HIST_THREADS, 0, st>>>(src, pitch, fstride, g, rps, hist, luma, mm);
+            if (extra) k_luma_hist<1, true><<<grid, HIST_THREADS, 0, st>>>(s0, pitch, fstride, g, rps, h0, l0, m0);
+            else k_luma_hist<1, false><<<grid, HIST_THREADS, 0, st>>>(s0, pitch, fstride, g, rps, h0, l0, m0);
         } else {
-            if (extra) k_luma_hist<0, true><<<grid, HIST_THREADS, 0, st>>>(src, pitch, fstride, g, rps, hist, luma, mm);
-            else k_luma_hist<0, false><<<grid, HIST_THREADS, 0, st>>>(src, pitch, fstride, g, rps, hist, luma, mm);
+            if (extra) k_luma_hist<0, true><<<grid, HIST_THREADS, 0, st>>>(s0, pitch, fstride, g, rps, h0, l0, m0);
+            else k_luma_hist<0, false><<<grid, HIST_THREADS, 0, st>>>(s0, pitch, fstride, g, rps, h0, l0, m0);
         }
+        ctx->launches++;
     }
-    ctx->launches++;
     CK(cudaGetLastError());
     return RV_OK;
 }
@@ -327,44 +395,71 @@ int launch_lut(rv_ctx *ctx, const int32_t *hist, const Geo &g, double clip_limit
 {
     const int clip = clip_int(clip_limit, g);
     const float lut_scale = 255.0f / (float)(g.tw * g.th);
-    {
+    const size_t tiles = (size_t)g.grid * g.grid, nq = (size_t)(g.grid + 1) * (g.grid + 1);
+    for (int f0 = 0; f0 < n; f0 += MAX_FRAMES_PER_LAUNCH) {
+        const int nf = std::min(MAX_FRAMES_PER_LAUNCH, n - f0);
+        const int32_t *h0 = hist + (size_t)f0 * tiles * 256;
+        uint8_t *l0 = lut ? lut + (size_t)f0 * tiles * 256 : nullptr;
+        uint32_t *q0 = quads + (size_t)f0 * nq * 256;
         ScopedTiming tm(ctx, st, 1);
         if (g.grid <= LUT_ROWS_MAX_GRID)
-            k_build_lut_rows<<<dim3(g.grid + 1, n), 64 * g.grid, 0, st>>>(hist, g.grid, clip, lut_scale, lut, quads);
+            k_build_lut_rows<<<dim3(g.grid + 1, nf), 64 * g.grid, 0, st>>>(h0, g.grid, clip, lut_scale, l0, q0);
         else
-            k_build_lut<<<dim3((g.grid + 1) * (g.grid + 1), n), 128, 0, st>>>(hist, g.grid, clip, lut_scale, lut, quads);
+            k_build_lut<<<dim3((g.grid + 1) * (g.grid + 1), nf), 128, 0, st>>>(h0, g.grid, clip, lut_scale, l0, q0);
+        ctx->launches++;
     }
-    ctx->launches++;
     CK(cudaGetLastError());
     return RV_OK;
 }
 
-// Column records for k_chain (A.3 horizontal terms), rebuilt only when (W, tile width) changes.  Record r describes
+// A geometry table is uploaded on the stream that first needs it (page-locked host copy kept with the entry) and is read-only
+// afterwards; other streams wait for the upload event.  Nothing synchronises the device.
+int flush_tables(rv_ctx *ctx)
+{
+    CK(cudaDeviceSynchronize());            // rare: more than MAX_TABS geometries seen by one context
+    for (ColTab &t : ctx->coltabs) { cudaFree(t.dev); cudaFreeHost(t.host); cudaEventDestroy(t.ready); }
+    for (LbTab &t : ctx->lbtabs) { cudaFree(t.dev); cudaFreeHost(t.host); cudaEventDestroy(t.ready); }
+    ctx->coltabs.clear();
+    ctx->lbtabs.clear();
+    return RV_OK;
+}
+
+// Column records for k_chain (A.3 horizontal terms), built once per (W, tile width).  Record r describes
 // the four pixels 4*(r-1) .. 4*(r-1)+3 (clamped into the frame): xa, xa1 = 1 - xa, -2^23*xa, -2^23*xa1, quad column.
 // Every value is produced by single IEEE-754 binary32 operations, exactly as the kernel used to compute them.
-int build_colparams(rv_ctx *ctx, const Geo &g, cudaStream_t st)
+int get_colparams(rv_ctx *ctx, const Geo &g, cudaStream_t st, const float **out)
 {
-    if (ctx->colp_w == g.W && ctx->colp_tw == g.tw && ctx->colp.p) return RV_OK;
+    for (ColTab &t : ctx->coltabs)
+        if (t.w == g.W && t.tw == g.tw) {
+            if (t.up != st) CK(cudaStreamWaitEvent(st, t.ready, 0));
+            *out = t.dev;
+            return RV_OK;
+        }
+    if ((int)ctx->coltabs.size() >= MAX_TABS) RV_TRY(flush_tables(ctx));
     const int ngroups = (TILE_W / 4) * ((g.W + TILE_W - 1) / TILE_W) + 34;
-    std::vector<float> tab((size_t)ngroups * 20);
+    const size_t bytes = (size_t)ngroups * 20 * 4;
+    ColTab t;
+    t.w = g.W; t.tw = g.tw; t.up = st;
+    CK(cudaHostAlloc((void **)&t.host, bytes, cudaHostAllocDefault));
+    if (cudaMalloc((void **)&t.dev, bytes) != cudaSuccess) { cudaFreeHost(t.host); return fail(ctx, RV_ERR_NOMEM, "cudaMalloc(column records)"); }
+    if (cudaEventCreateWithFlags(&t.ready, cudaEventDisableTiming) != cudaSuccess) { cudaFree(t.dev); cudaFreeHost(t.host); return fail(ctx, RV_ERR_CUDA, "cudaEventCreate"); }
     for (int r = 0; r < ngroups; ++r)
         for (int j = 0; j < 4; ++j) {
             const int cx = std::min(std::max(4 * (r - 1) + j, 0), g.W - 1);
-            volatile float t = (float)cx * g.inv_tw;
-            volatile float txf = t - 0.5f;
+            volatile float tt = (float)cx * g.inv_tw;
+            volatile float txf = tt - 0.5f;
             const float fl = floorf(txf);
             volatile float xa = txf - fl;
             volatile float xa1 = 1.0f - xa;
-            float *rec = &tab[(size_t)r * 20];
+            float *rec = &t.host[(size_t)r * 20];
             rec[j] = xa; rec[4 + j] = xa1; rec[8 + j] = -8388608.0f * xa; rec[12 + j] = -8388608.0f * xa1;
             const int q = (int)fl + 1;
             memcpy(&rec[16 + j], &q, 4);
         }
-    RV_TRY(ensure(ctx, ctx->colp, tab.size() * 4));
-    (void)st;
-    CK(cudaDeviceSynchronize());            // rare path (geometry changed): nothing may still be reading the old table
-    CK(cudaMemcpy(ctx->colp.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
-    ctx->colp_w = g.W; ctx->colp_tw = g.tw;
+    ctx->coltabs.push_back(t);
+    CK(cudaMemcpyAsync(t.dev, t.host, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(t.ready, st));
+    *out = t.dev;
     return RV_OK;
 }
 
@@ -379,6 +474,11 @@ int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs
 {
     // st_pre (optional): histogram / LUT / gate flags run there and `st` waits for them before k_chain
     cudaStream_t sp = st_pre ? st_pre : st;
+    // the previous user of this workspace set may have been on another stream (two caller streams, or a stage-level call)
+    WsSync &wsy = ctx->wsync[ws];
+    if (wsy.used && wsy.last != sp) CK(cudaStreamWaitEvent(sp, wsy.ev, 0));
+    if (wsy.used && st != sp && wsy.last != st) CK(cudaStreamWaitEvent(st, wsy.ev, 0));
+    const int gate_t = gate_thresh_int(p->gate_thresh);
     ChainArgs a;
     a.src = din; a.spitch = ipitch; a.sfstride = ifs;
     a.dst = dout; a.dpitch = opitch; a.dfstride = ofs;
@@ -395,7 +495,7 @@ int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs
             RV_TRY(ensure(ctx, ctx->flags[ws], (size_t)n * 4));
             RV_TRY(launch_hist(ctx, din, ipitch, ifs, a.g, RV_SPACE_YCRCB, n, (int32_t *)ctx->hist[ws].p, nullptr,
                                (int32_t *)ctx->mm[ws].p, sp));
-            k_gate_flags<<<(n + 127) / 128, 128, 0, sp>>>((int32_t *)ctx->mm[ws].p, n, (float)p->gate_thresh, (int32_t *)ctx->flags[ws].p);
+            k_gate_flags<<<(n + 127) / 128, 128, 0, sp>>>((int32_t *)ctx->mm[ws].p, n, gate_t, (int32_t *)ctx->flags[ws].p);
             ctx->launches++;
             a.flags = (int32_t *)ctx->flags[ws].p;
         }
@@ -415,7 +515,7 @@ int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs
         RV_TRY(launch_hist(ctx, din, ipitch, ifs, g, p->space, n, (int32_t *)ctx->hist[ws].p, nullptr, mm, sp));
         RV_TRY(launch_lut(ctx, (int32_t *)ctx->hist[ws].p, g, p->clip_limit, n, nullptr, (uint32_t *)ctx->quads[ws].p, sp));
         if (p->gate_enable) {
-            k_gate_flags<<<(n + 127) / 128, 128, 0, sp>>>(mm, n, (float)p->gate_thresh, (int32_t *)ctx->flags[ws].p);
+            k_gate_flags<<<(n + 127) / 128, 128, 0, sp>>>(mm, n, gate_t, (int32_t *)ctx->flags[ws].p);
             ctx->launches++;
             a.flags = (int32_t *)ctx->flags[ws].p;
         }
@@ -424,17 +524,39 @@ int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs
             CK(cudaEventRecord(ev_pre, st_pre));
             CK(cudaStreamWaitEvent(st, ev_pre, 0));
         }
-        RV_TRY(build_colparams(ctx, g, st));
-        a.colp = (const float *)ctx->colp.p;
+        RV_TRY(get_colparams(ctx, g, st, &a.colp));
         RV_TRY(launch_chain(ctx, p->space == RV_SPACE_LAB ? 1 : 0, a, n, p->ksize, st));
     }
     if (a.flags) {
-        dim3 grid(4, std::min(h, 64), n);
-        k_gate_copy<<<grid, 256, 0, st>>>(din, ipitch, ifs, dout, opitch, ofs, h, 3 * w, a.flags);
-        ctx->launches++;
+        for (int f0 = 0; f0 < n; f0 += MAX_FRAMES_PER_LAUNCH) {
+            dim3 grid(4, std::min(h, 64), std::min(MAX_FRAMES_PER_LAUNCH, n - f0));
+            k_gate_copy<<<grid, 256, 0, st>>>(din + (size_t)f0 * ifs, ipitch, ifs, dout + (size_t)f0 * ofs, opitch, ofs, h, 3 * w,
+                                              a.flags + f0);
+            ctx->launches++;
+        }
         if (flags_out) *flags_out = (int32_t *)ctx->flags[ws].p;
     }
     CK(cudaGetLastError());
+    CK(cudaEventRecord(wsy.ev, st));        // (a caller that reads the flags afterwards records it again, see ws_release)
+    wsy.last = st;
+    wsy.used = true;
+    return RV_OK;
+}
+
+// re-arm the ordering event of a workspace set after more work that reads it has been queued on `st`
+int ws_release(rv_ctx *ctx, int ws, cudaStream_t st)
+{
+    WsSync &wsy = ctx->wsync[ws];
+    CK(cudaEventRecord(wsy.ev, st));
+    wsy.last = st;
+    wsy.used = true;
+    return RV_OK;
+}
+
+int ws_acquire(rv_ctx *ctx, int ws, cudaStream_t st)
+{
+    WsSync &wsy = ctx->wsync[ws];
+    if (wsy.used && wsy.last != st) CK(cudaStreamWaitEvent(st, wsy.ev, 0));
     return RV_OK;
 }
 
@@ -465,7 +587,6 @@ int chain_device(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int
     if (overlap) {
         const int ng = (int)ctx->overlap_groups;
         const int per = (n + ng - 1) / ng;
-        RV_TRY(build_colparams(ctx, make_geo(h, w, p->grid), st));      // before any asynchronous work is queued
         CK(cudaEventRecord(ctx->ev_entry, st));
         CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_entry, 0));
         int gi = 0;
@@ -491,42 +612,6 @@ int chain_device(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int
             } else {
                 for (int i = 0; i < g; ++i) processed_host[f0 + i] = 1;
             }
-        }
-    }
-    return RV_OK;
-}
-
-// host buffers: chunks of frames flow H2D -> kernels -> D2H on NPIPE streams
-int chain_host(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w, size_t ipitch, size_t opitch,
-               const rv_params *p, int32_t *processed_host)
-{
-    const long C = std::min<long>(auto_chunk(ctx, h, w), std::max(1, n));
-    const size_t rowb = (size_t)3 * w;
-    const size_t dpitch = (rowb + 15) & ~(size_t)15;
-    const size_t dfs = dpitch * h;
-    for (int i = 0; i < NPIPE; ++i) {
-        RV_TRY(ensure(ctx, ctx->din[i], dfs * C));
-        RV_TRY(ensure(ctx, ctx->dout[i], dfs * C));
-    }
-    int chunk = 0;
-    for (int f0 = 0; f0 < n; f0 += (int)C, ++chunk) {
-        const int s = chunk % NPIPE;
-        const int g = (int)std::min<long>(C, n - f0);
-        cudaStream_t st = ctx->pipe[s];
-        uint8_t *di = (uint8_t *)ctx->din[s].p, *dout = (uint8_t *)ctx->dout[s].p;
-        if (ipitch == dpitch)
-            CK(cudaMemcpyAsync(di, in + (size_t)f0 * ipitch * h, dfs * g, cudaMemcpyHostToDevice, st));
-        else
-            CK(cudaMemcpy2DAsync(di, dpitch, in + (size_t)f0 * ipitch * h, ipitch, rowb, (size_t)h * g, cudaMemcpyHostToDevice, st));
-        int32_t *flags = nullptr;
-        RV_TRY(run_group(ctx, s, di, dpitch, dfs, dout, dpitch, dfs, g, h, w, p, st, &flags));
-        if (opitch == dpitch)
-            CK(cudaMemcpyAsync(out + (size_t)f0 * opitch * h, dout, dfs * g, cudaMemcpyDeviceToHost, st));
-        else
-            CK(cudaMemcpy2DAsync(out + (size_t)f0 * opitch * h, opitch, dout, dpitch, rowb, (size_t)h * g, cudaMemcpyDeviceToHost, st));
-        if (processed_host) {
-            if (flags) CK(cudaMemcpyAsync(processed_host + f0, flags, (size_t)g * 4, cudaMemcpyDeviceToHost, st));
-            else for (int i = 0; i < g; ++i) processed_host[f0 + i] = 1;
         }
     }
     return RV_OK;
@@ -600,11 +685,9 @@ LbGeo lb_geometry(int h, int w, int S)
 
 // cv2.resize(INTER_LINEAR) tables for 8-bit data (resize.cpp): x clamps with the fraction forced to 0,
 // y keeps the fraction and clips the two row indices; coefficients are cvRound(c * 2048) as shorts.
-void lb_tables(int ssize, int dsize, bool is_x, std::vector<int32_t> &ofs, std::vector<int16_t> &coef)
+void lb_tables(int ssize, int dsize, bool is_x, int32_t *ofs, int16_t *coef)
 {
     const double scale = 1.0 / ((double)dsize / ssize);
-    ofs.assign(is_x ? dsize : 2 * dsize, 0);
-    coef.assign(2 * dsize, 0);
     for (int d = 0; d < dsize; ++d) {
         float f = (float)((d + 0.5) * scale - 0.5);
         int sidx = (int)floorf(f);
@@ -622,6 +705,36 @@ void lb_tables(int ssize, int dsize, bool is_x, std::vector<int32_t> &ofs, std::
     }
 }
 
+// the four resize tables of one (h, w) -> (nh, nw) geometry, cached like the column records (see get_colparams)
+int get_lbtab(rv_ctx *ctx, int h, int w, const LbGeo &g, cudaStream_t st, const LbTab **out)
+{
+    for (LbTab &t : ctx->lbtabs)
+        if (t.h == h && t.w == w && t.nh == g.nh && t.nw == g.nw) {
+            if (t.up != st) CK(cudaStreamWaitEvent(st, t.ready, 0));
+            *out = &t;
+            return RV_OK;
+        }
+    if ((int)ctx->lbtabs.size() >= MAX_TABS) RV_TRY(flush_tables(ctx));
+    auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    LbTab t;
+    t.h = h; t.w = w; t.nh = g.nh; t.nw = g.nw; t.up = st;
+    t.o_yofs = up16((size_t)g.nw * 4);
+    t.o_xa = t.o_yofs + up16((size_t)2 * g.nh * 4);
+    t.o_ya = t.o_xa + up16((size_t)2 * g.nw * 2);
+    const size_t bytes = t.o_ya + up16((size_t)2 * g.nh * 2);
+    CK(cudaHostAlloc((void **)&t.host, bytes, cudaHostAllocDefault));
+    if (cudaMalloc((void **)&t.dev, bytes) != cudaSuccess) { cudaFreeHost(t.host); return fail(ctx, RV_ERR_NOMEM, "cudaMalloc(letterbox tables)"); }
+    if (cudaEventCreateWithFlags(&t.ready, cudaEventDisableTiming) != cudaSuccess) { cudaFree(t.dev); cudaFreeHost(t.host); return fail(ctx, RV_ERR_CUDA, "cudaEventCreate"); }
+    memset(t.host, 0, bytes);
+    lb_tables(w, g.nw, true, (int32_t *)t.host, (int16_t *)(t.host + t.o_xa));
+    lb_tables(h, g.nh, false, (int32_t *)(t.host + t.o_yofs), (int16_t *)(t.host + t.o_ya));
+    ctx->lbtabs.push_back(t);
+    CK(cudaMemcpyAsync(t.dev, t.host, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(t.ready, st));
+    *out = &ctx->lbtabs.back();
+    return RV_OK;
+}
+
 int launch_letterbox(rv_ctx *ctx, const uint8_t *src, size_t pitch, size_t fstride, int n, int h, int w, const LbGeo &g,
                      int pad, bool only_pad, uint16_t *out, cudaStream_t st)
 {
@@ -630,26 +743,109 @@ int launch_letterbox(rv_ctx *ctx, const uint8_t *src, size_t pitch, size_t fstri
     a.H = h; a.W = w; a.S = g.S; a.nw = g.nw; a.nh = g.nh; a.top = g.top; a.left = g.left; a.pad = pad; a.only_pad = only_pad ? 1 : 0;
     a.xofs = nullptr; a.xa = nullptr; a.yofs = nullptr; a.ya = nullptr;
     if (!only_pad) {
-        std::vector<int32_t> xo, yo;
-        std::vector<int16_t> xa, ya;
-        lb_tables(w, g.nw, true, xo, xa);
-        lb_tables(h, g.nh, false, yo, ya);
-        const size_t b0 = xo.size() * 4, b1 = yo.size() * 4, b2 = xa.size() * 2, b3 = ya.size() * 2;
-        RV_TRY(ensure(ctx, ctx->lbtab, b0 + b1 + b2 + b3 + 64));
-        uint8_t *base = (uint8_t *)ctx->lbtab.p;
-        // the tables are tiny; a synchronous copy keeps the host vectors alive for exactly as long as needed
-        CK(cudaStreamSynchronize(st));
-        CK(cudaMemcpy(base, xo.data(), b0, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(base + b0, yo.data(), b1, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(base + b0 + b1, xa.data(), b2, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(base + b0 + b1 + b2, ya.data(), b3, cudaMemcpyHostToDevice));
-        a.xofs = (const int32_t *)base; a.yofs = (const int32_t *)(base + b0);
-        a.xa = (const int16_t *)(base + b0 + b1); a.ya = (const int16_t *)(base + b0 + b1 + b2);
+        const LbTab *t = nullptr;
+        RV_TRY(get_lbtab(ctx, h, w, g, st, &t));
+        a.xofs = (const int32_t *)t->dev; a.yofs = (const int32_t *)(t->dev + t->o_yofs);
+        a.xa = (const int16_t *)(t->dev + t->o_xa); a.ya = (const int16_t *)(t->dev + t->o_ya);
     }
-    dim3 grid((g.S + 31) / 32, (g.S + 7) / 8, n), block(32, 8);
-    k_letterbox<<<grid, block, 0, st>>>(a);
-    ctx->launches++;
+    for (int f0 = 0; f0 < n; f0 += MAX_FRAMES_PER_LAUNCH) {
+        LbArgs b = a;
+        if (b.src) b.src += (size_t)f0 * fstride;
+        b.out += (size_t)f0 * 3 * g.S * g.S;
+        dim3 grid((g.S + 31) / 32, (g.S + 7) / 8, std::min(MAX_FRAMES_PER_LAUNCH, n - f0)), block(32, 8);
+        k_letterbox<<<grid, block, 0, st>>>(b);
+        ctx->launches++;
+    }
     CK(cudaGetLastError());
+    return RV_OK;
+}
+
+// ---- the chunked pipeline for jobs that touch host memory ----------------------------------------------------
+// Chunks of frames flow  H2D -> kernels -> D2H  on NPIPE streams, so the copies of consecutive chunks overlap with each other
+// and with the kernels.  Every end of the job may independently live on the host or on the device: a device input skips the
+// H2D, a device output / tensor skips its D2H (results that the next stage consumes on the same GPU never cross PCIe).
+struct PipeJob {
+    const uint8_t *in = nullptr; int in_kind = RV_MEM_HOST; size_t ipitch = 0;
+    uint8_t *out = nullptr; int out_kind = RV_MEM_HOST; size_t opitch = 0;      // full-resolution result; nullptr = not wanted
+    uint16_t *lb = nullptr; int lb_kind = RV_MEM_HOST; int S = 0, pad = 114;     // detector tensor; nullptr = none
+    int32_t *processed = nullptr;                                               // host, optional
+};
+
+int chain_pipe(rv_ctx *ctx, const PipeJob &j, int n, int h, int w, const rv_params *p)
+{
+    const long C = std::min<long>(std::min<long>(auto_chunk(ctx, h, w), std::max(1, n)), 4096);
+    const size_t rowb = (size_t)3 * w;
+    const size_t dpitch = (rowb + 15) & ~(size_t)15;
+    const size_t dfs = dpitch * h;
+    const bool in_dev = j.in_kind == RV_MEM_DEVICE, out_dev = j.out_kind == RV_MEM_DEVICE, lb_dev = j.lb_kind == RV_MEM_DEVICE;
+    LbGeo lg = {};
+    size_t lbf = 0;                                         // halves per frame of the detector tensor
+    if (j.lb) {
+        lg = lb_geometry(h, w, j.S);
+        lbf = (size_t)3 * j.S * j.S;
+    }
+    const bool fused = j.lb && lg.scale > 0;
+    const bool need_dfull = (j.out && !out_dev) || (j.lb && !fused && !(j.out && out_dev));   // a device staging copy of the full result
+    for (int i = 0; i < NPIPE; ++i) {
+        if (!in_dev) RV_TRY(ensure(ctx, ctx->din[i], dfs * C));
+        if (need_dfull) RV_TRY(ensure(ctx, ctx->dout[i], dfs * C));
+        if (j.lb && !lb_dev) RV_TRY(ensure(ctx, ctx->dlb[i], lbf * 2 * C));
+    }
+    int chunk = 0;
+    for (int f0 = 0; f0 < n; f0 += (int)C, ++chunk) {
+        const int s = chunk % NPIPE;
+        const int g = (int)std::min<long>(C, n - f0);
+        cudaStream_t st = ctx->pipe[s];
+        // input
+        const uint8_t *di;
+        size_t dip, difs;
+        if (in_dev) {
+            di = j.in + (size_t)f0 * j.ipitch * h; dip = j.ipitch; difs = j.ipitch * h;
+        } else {
+            uint8_t *d = (uint8_t *)ctx->din[s].p;
+            if (j.ipitch == dpitch)
+                CK(cudaMemcpyAsync(d, j.in + (size_t)f0 * j.ipitch * h, dfs * g, cudaMemcpyHostToDevice, st));
+            else
+                CK(cudaMemcpy2DAsync(d, dpitch, j.in + (size_t)f0 * j.ipitch * h, j.ipitch, rowb, (size_t)h * g, cudaMemcpyHostToDevice, st));
+            di = d; dip = dpitch; difs = dfs;
+        }
+        // where the kernels write
+        uint8_t *dfull = nullptr;
+        size_t dop = dpitch, dofs = dfs;
+        if (j.out && out_dev) { dfull = j.out + (size_t)f0 * j.opitch * h; dop = j.opitch; dofs = j.opitch * h; }
+        else if (need_dfull) dfull = (uint8_t *)ctx->dout[s].p;
+        uint16_t *dl = nullptr;
+        if (j.lb) dl = lb_dev ? j.lb + (size_t)f0 * lbf : (uint16_t *)ctx->dlb[s].p;
+        int32_t *flags = nullptr;
+        if (fused) {
+            LbFused lb = {dl, lg.scale, j.S, lg.top, lg.left, j.out ? 1 : 0};
+            RV_TRY(launch_letterbox(ctx, nullptr, 0, 0, g, h, w, lg, j.pad, true, dl, st));
+            RV_TRY(run_group(ctx, s, di, dip, difs, j.out ? dfull : (uint8_t *)dl, j.out ? dop : dip, j.out ? dofs : difs, g, h, w, p, st,
+                             &flags, &lb));
+        } else {
+            RV_TRY(run_group(ctx, s, di, dip, difs, dfull, dop, dofs, g, h, w, p, st, &flags));
+            if (j.lb) RV_TRY(launch_letterbox(ctx, dfull, dop, dofs, g, h, w, lg, j.pad, false, dl, st));
+        }
+        // results
+        if (j.out && !out_dev) {
+            if (j.opitch == dpitch)
+                CK(cudaMemcpyAsync(j.out + (size_t)f0 * j.opitch * h, dfull, dfs * g, cudaMemcpyDeviceToHost, st));
+            else
+                CK(cudaMemcpy2DAsync(j.out + (size_t)f0 * j.opitch * h, j.opitch, dfull, dpitch, rowb, (size_t)h * g, cudaMemcpyDeviceToHost, st));
+        }
+        if (j.lb && !lb_dev) CK(cudaMemcpyAsync(j.lb + (size_t)f0 * lbf, dl, lbf * 2 * g, cudaMemcpyDeviceToHost, st));
+        if (j.processed) {
+            if (flags) CK(cudaMemcpyAsync(j.processed + f0, flags, (size_t)g * 4, cudaMemcpyDeviceToHost, st));
+            else for (int i = 0; i < g; ++i) j.processed[f0 + i] = 1;
+        }
+        RV_TRY(ws_release(ctx, s, st));
+    }
+    return RV_OK;
+}
+
+int check_lb_args(rv_ctx *ctx, const void *tensor, int S, int pad_value)
+{
+    if (!tensor || S < 1 || S > 8192 || pad_value < 0 || pad_value > 255) return fail(ctx, RV_ERR_ARG, "bad letterbox arguments");
     return RV_OK;
 }
 
@@ -699,6 +895,8 @@ int rv_create(int device, rv_ctx **out)
         cudaEvent_t *evs[] = {&ctx->ev_entry, &ctx->ev_pre[0], &ctx->ev_pre[1], &ctx->ev_chain[0], &ctx->ev_chain[1]};
         for (cudaEvent_t *e : evs)
             if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
+        for (WsSync &w : ctx->wsync)
+            if (cudaEventCreateWithFlags(&w.ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
     }
     // LAB tables
     LabTabs *t = new (std::nothrow) LabTabs();
@@ -735,10 +933,14 @@ void rv_destroy(rv_ctx *ctx)
     for (Buf *set : sets)
         for (int i = 0; i <= NPIPE + 1; ++i)
             if (set[i].p) cudaFree(set[i].p);
+    for (Buf &b : ctx->dlb)
+        if (b.p) cudaFree(b.p);
     if (ctx->scratch.p) cudaFree(ctx->scratch.p);
-    if (ctx->lbtab.p) cudaFree(ctx->lbtab.p);
-    if (ctx->colp.p) cudaFree(ctx->colp.p);
     if (ctx->lbfull.p) cudaFree(ctx->lbfull.p);
+    for (ColTab &t : ctx->coltabs) { cudaFree(t.dev); cudaFreeHost(t.host); cudaEventDestroy(t.ready); }
+    for (LbTab &t : ctx->lbtabs) { cudaFree(t.dev); cudaFreeHost(t.host); cudaEventDestroy(t.ready); }
+    for (WsSync &w : ctx->wsync)
+        if (w.ev) cudaEventDestroy(w.ev);
     for (const TimedLaunch &t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < NPIPE; ++i)
@@ -847,18 +1049,65 @@ int rv_kernel_time_reset(rv_ctx *ctx)
     return RV_OK;
 }
 
-int rv_submit(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w, size_t in_pitch, size_t out_pitch,
-              const rv_params *p, int mem_kind, void *stream)
+namespace {
+int check_kind(rv_ctx *ctx, int kind)
+{
+    if (kind != RV_MEM_HOST && kind != RV_MEM_HOST_PINNED && kind != RV_MEM_DEVICE) return fail(ctx, RV_ERR_ARG, "bad memory kind %d", kind);
+    return RV_OK;
+}
+int check_chain_call(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w, size_t in_pitch, size_t out_pitch, const rv_params *p)
 {
     RV_TRY(check_frames(ctx, in, out, n, h, w, in_pitch, out_pitch));
     RV_TRY(check_params(ctx, p));
     if (!p->clahe && p->ksize == 0) return fail(ctx, RV_ERR_ARG, "nothing to do (no CLAHE, no median)");
     if (in == out) return fail(ctx, RV_ERR_ARG, "in-place operation is not supported (tiles read their neighbours' halo)");
+    return RV_OK;
+}
+}  // namespace
+
+int rv_submit(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w, size_t in_pitch, size_t out_pitch,
+              const rv_params *p, int mem_kind, void *stream)
+{
+    RV_TRY(check_chain_call(ctx, in, out, n, h, w, in_pitch, out_pitch, p));
+    RV_TRY(check_kind(ctx, mem_kind));
     if (n == 0) return RV_OK;
     CK(cudaSetDevice(ctx->device));
     if (mem_kind == RV_MEM_DEVICE)
         return chain_device(ctx, in, out, n, h, w, in_pitch, out_pitch, p, nullptr, stream ? (cudaStream_t)stream : ctx->stream);
-    return chain_host(ctx, in, out, n, h, w, in_pitch, out_pitch, p, nullptr);
+    PipeJob j;
+    j.in = in; j.in_kind = mem_kind; j.ipitch = in_pitch;
+    j.out = out; j.out_kind = mem_kind; j.opitch = out_pitch;
+    return chain_pipe(ctx, j, n, h, w, p);
+}
+
+int rv_submit_io(rv_ctx *ctx, const rv_io *io, int n, int h, int w, const rv_params *p)
+{
+    if (!ctx) return RV_ERR_ARG;
+    if (!io) return fail(ctx, RV_ERR_ARG, "null rv_io");
+    if (!io->in) return fail(ctx, RV_ERR_ARG, "null frame pointer");
+    if (!io->out && !io->tensor) return fail(ctx, RV_ERR_ARG, "neither a frame output nor a tensor output was given");
+    RV_TRY(check_kind(ctx, io->in_kind));
+    // with no frame output the input stands in for it in the shape / pitch checks
+    RV_TRY(check_frames(ctx, io->in, io->out ? io->out : io->in, n, h, w, io->in_pitch, io->out ? io->out_pitch : io->in_pitch));
+    RV_TRY(check_params(ctx, p));
+    if (!p->clahe && p->ksize == 0) return fail(ctx, RV_ERR_ARG, "nothing to do (no CLAHE, no median)");
+    if (io->out) {
+        RV_TRY(check_kind(ctx, io->out_kind));
+        if (io->in == io->out) return fail(ctx, RV_ERR_ARG, "in-place operation is not supported (tiles read their neighbours' halo)");
+    }
+    if (io->tensor) {
+        RV_TRY(check_kind(ctx, io->tensor_kind));
+        RV_TRY(check_lb_args(ctx, io->tensor, io->tensor_size, io->pad_value));
+        if (p->gate_enable) return fail(ctx, RV_ERR_ARG, "the gate is not supported together with the letterbox stage");
+    }
+    if (n == 0) return RV_OK;
+    CK(cudaSetDevice(ctx->device));
+    PipeJob j;
+    j.in = io->in; j.in_kind = io->in_kind; j.ipitch = io->in_pitch;
+    j.out = io->out; j.out_kind = io->out_kind; j.opitch = io->out_pitch;
+    j.lb = io->tensor; j.lb_kind = io->tensor_kind; j.S = io->tensor_size; j.pad = io->pad_value;
+    j.processed = io->processed;
+    return chain_pipe(ctx, j, n, h, w, p);
 }
 
 int rv_wait(rv_ctx *ctx) { return rv_sync(ctx); }
@@ -866,10 +1115,8 @@ int rv_wait(rv_ctx *ctx) { return rv_sync(ctx); }
 int rv_chain_u8(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int w, size_t in_pitch, size_t out_pitch,
                 const rv_params *p, int mem_kind, int32_t *processed, void *stream)
 {
-    RV_TRY(check_frames(ctx, in, out, n, h, w, in_pitch, out_pitch));
-    RV_TRY(check_params(ctx, p));
-    if (!p->clahe && p->ksize == 0) return fail(ctx, RV_ERR_ARG, "nothing to do (no CLAHE, no median)");
-    if (in == out) return fail(ctx, RV_ERR_ARG, "in-place operation is not supported (tiles read their neighbours' halo)");
+    RV_TRY(check_chain_call(ctx, in, out, n, h, w, in_pitch, out_pitch, p));
+    RV_TRY(check_kind(ctx, mem_kind));
     if (n == 0) return RV_OK;
     CK(cudaSetDevice(ctx->device));
     if (mem_kind == RV_MEM_DEVICE) {
@@ -878,7 +1125,11 @@ int rv_chain_u8(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int 
         CK(cudaStreamSynchronize(st));
         return RV_OK;
     }
-    RV_TRY(chain_host(ctx, in, out, n, h, w, in_pitch, out_pitch, p, processed));
+    PipeJob j;
+    j.in = in; j.in_kind = mem_kind; j.ipitch = in_pitch;
+    j.out = out; j.out_kind = mem_kind; j.opitch = out_pitch;
+    j.processed = processed;
+    RV_TRY(chain_pipe(ctx, j, n, h, w, p));
     return wait_all(ctx);
 }
 
@@ -976,48 +1227,45 @@ int rv_letterbox_f16(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t
 int rv_chain_letterbox_f16(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t in_pitch, const rv_params *p,
                            uint16_t *out, int S, int pad_value, uint8_t *full_out, size_t full_pitch, int mem_kind, void *stream)
 {
-    RV_TRY(check_frames(ctx, in, in, n, h, w, in_pitch, in_pitch));
+    RV_TRY(check_frames(ctx, in, full_out ? full_out : in, n, h, w, in_pitch, full_out ? full_pitch : in_pitch));
     RV_TRY(check_params(ctx, p));
+    RV_TRY(check_kind(ctx, mem_kind));
     if (!p->clahe && p->ksize == 0) return fail(ctx, RV_ERR_ARG, "nothing to do (no CLAHE, no median)");
     if (p->gate_enable) return fail(ctx, RV_ERR_ARG, "the gate is not supported together with the letterbox stage");
-    if (!out || S < 1 || S > 8192 || pad_value < 0 || pad_value > 255) return fail(ctx, RV_ERR_ARG, "bad letterbox arguments");
-    if (full_out && full_pitch < (size_t)3 * w) return fail(ctx, RV_ERR_ARG, "pitch smaller than 3*w");
+    RV_TRY(check_lb_args(ctx, out, S, pad_value));
+    if (full_out && in == full_out) return fail(ctx, RV_ERR_ARG, "in-place operation is not supported (tiles read their neighbours' halo)");
     if (n == 0) return RV_OK;
     CK(cudaSetDevice(ctx->device));
+    if (mem_kind != RV_MEM_DEVICE) {
+        // host buffers: the chunked H2D / kernels / D2H pipeline; only the tensor (and the frames, if asked for) come back
+        PipeJob j;
+        j.in = in; j.in_kind = mem_kind; j.ipitch = in_pitch;
+        j.out = full_out; j.out_kind = mem_kind; j.opitch = full_pitch;
+        j.lb = out; j.lb_kind = mem_kind; j.S = S; j.pad = pad_value;
+        RV_TRY(chain_pipe(ctx, j, n, h, w, p));
+        return wait_all(ctx);
+    }
     const LbGeo g = lb_geometry(h, w, S);
-    cudaStream_t st = (mem_kind == RV_MEM_DEVICE && stream) ? (cudaStream_t)stream : ctx->stream;
-    const size_t ob = (size_t)n * 3 * S * S * 2, fb = full_pitch * h * n;
-    Staged si, so, sf;
-    RV_TRY(stage_in(ctx, si, in, in_pitch * h * n, mem_kind));
-    RV_TRY(stage_out(ctx, so, out, ob, mem_kind));
-    uint8_t *dfull = nullptr;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    uint8_t *dfull = full_out;
     size_t dpitch = full_pitch;
-    if (full_out) {
-        RV_TRY(stage_out(ctx, sf, full_out, fb, mem_kind));
-        dfull = (uint8_t *)sf.dev;
-    } else if (g.scale == 0) {
+    if (!full_out && g.scale == 0) {
         dpitch = ((size_t)3 * w + 15) & ~(size_t)15;        // unfused: the resize reads a full-resolution intermediate
+        RV_TRY(ws_acquire(ctx, NPIPE, st));                 // lbfull belongs to workspace set NPIPE
         RV_TRY(ensure(ctx, ctx->lbfull, dpitch * h * n));
         dfull = (uint8_t *)ctx->lbfull.p;
     }
-    const uint8_t *din = (const uint8_t *)si.dev;
     if (g.scale > 0) {
-        LbFused lb = {(uint16_t *)so.dev, g.scale, S, g.top, g.left, dfull ? 1 : 0};
-        RV_TRY(launch_letterbox(ctx, din, in_pitch, in_pitch * h, n, h, w, g, pad_value, true, (uint16_t *)so.dev, st));
-        RV_TRY(run_group(ctx, NPIPE, din, in_pitch, in_pitch * h, dfull ? dfull : (uint8_t *)so.dev, dfull ? dpitch : in_pitch,
+        LbFused lb = {out, g.scale, S, g.top, g.left, dfull ? 1 : 0};
+        RV_TRY(launch_letterbox(ctx, nullptr, 0, 0, n, h, w, g, pad_value, true, out, st));
+        RV_TRY(run_group(ctx, NPIPE, in, in_pitch, in_pitch * h, dfull ? dfull : (uint8_t *)out, dfull ? dpitch : in_pitch,
                          dfull ? dpitch * h : in_pitch * h, n, h, w, p, st, nullptr, &lb));
     } else {
-        RV_TRY(run_group(ctx, NPIPE, din, in_pitch, in_pitch * h, dfull, dpitch, dpitch * h, n, h, w, p, st, nullptr, nullptr));
-        RV_TRY(launch_letterbox(ctx, dfull, dpitch, dpitch * h, n, h, w, g, pad_value, false, (uint16_t *)so.dev, st));
+        RV_TRY(run_group(ctx, NPIPE, in, in_pitch, in_pitch * h, dfull, dpitch, dpitch * h, n, h, w, p, st, nullptr, nullptr));
+        RV_TRY(launch_letterbox(ctx, dfull, dpitch, dpitch * h, n, h, w, g, pad_value, false, out, st));
+        RV_TRY(ws_release(ctx, NPIPE, st));
     }
-    if (mem_kind != RV_MEM_DEVICE) {
-        CK(cudaStreamSynchronize(st));
-        RV_TRY(finish_out(ctx, so, out, ob, mem_kind));
-        if (full_out) RV_TRY(finish_out(ctx, sf, full_out, fb, mem_kind));
-        CK(cudaStreamSynchronize(ctx->stream));
-    } else if (!stream) {
-        CK(cudaStreamSynchronize(st));
-    }
+    if (!stream) CK(cudaStreamSynchronize(st));
     return RV_OK;
 }
 
@@ -1030,6 +1278,7 @@ int rv_gray_span(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t pit
     const Geo g = make_geo(h, w, 2);
     Staged si;
     RV_TRY(stage_in(ctx, si, in, pitch * h * n, mem_kind));
+    RV_TRY(ws_acquire(ctx, NPIPE, ctx->stream));
     RV_TRY(ensure(ctx, ctx->hist[NPIPE], (size_t)n * 4 * 256 * 4));
     RV_TRY(ensure(ctx, ctx->mm[NPIPE], (size_t)n * 8));
     RV_TRY(launch_hist(ctx, (const uint8_t *)si.dev, pitch, pitch * h, g, RV_SPACE_YCRCB, n, (int32_t *)ctx->hist[NPIPE].p, nullptr,
@@ -1037,6 +1286,9 @@ int rv_gray_span(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t pit
     int32_t *mm = new (std::nothrow) int32_t[2 * (size_t)n];
     if (!mm) return fail(ctx, RV_ERR_NOMEM, "host alloc");
     cudaError_t e = cudaMemcpyAsync(mm, ctx->mm[NPIPE].p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->wsync[NPIPE].ev, ctx->stream);
+    ctx->wsync[NPIPE].last = ctx->stream;
+    ctx->wsync[NPIPE].used = true;
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { delete[] mm; return fail(ctx, RV_ERR_CUDA, "gray span: %s", cudaGetErrorString(e)); }
     if (mem_kind == RV_MEM_DEVICE) {

@@ -14,7 +14,7 @@ namespace rv {
 
 // ---------------------------------------------------------------------------------------------
 // K1: luminance + per-tile histograms
-// grid = (slices, tiles, frames), block = 256.  With more than one slice per tile hist must be zeroed (the slices
+// grid = (tiles, slices, frames), block = 256.  With more than one slice per tile hist must be zeroed (the slices
 // accumulate with atomics); with one slice the CTA stores its bins.
 // ---------------------------------------------------------------------------------------------
 constexpr int HIST_THREADS = 256;
@@ -33,7 +33,7 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
     LabHistTabs *tabs = reinterpret_cast<LabHistTabs *>(tab_raw);
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int tile = blockIdx.y, f = blockIdx.z;
+    const int tile = blockIdx.x, f = blockIdx.z;
     const int ty = tile / g.grid, tx = tile - ty * g.grid;
     for (int i = tid; i < HIST_WARPS * 256; i += HIST_THREADS) (&wh[0][0])[i] = 0;
     if (SPACE == 1) {
@@ -44,7 +44,7 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
     __syncthreads();
 
     const uint8_t *frame = src + (size_t)f * fstride;
-    const int x0 = tx * g.tw, y0 = ty * g.th + blockIdx.x * rows_per_slice;
+    const int x0 = tx * g.tw, y0 = ty * g.th + blockIdx.y * rows_per_slice;
     const int y1 = min(y0 + rows_per_slice, (ty + 1) * g.th);
     const int nrows = y1 - y0;
     uint32_t *myh = wh[warp];
@@ -183,7 +183,7 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
 #pragma unroll
         for (int w = 0; w < HIST_WARPS; ++w) s += wh[w][tid];
         int32_t *bin = &hist[((size_t)f * g.grid * g.grid + tile) * 256 + tid];
-        if (gridDim.x == 1) *bin = (int)s;          // one CTA per tile: plain store, the buffer need not be zeroed
+        if (gridDim.y == 1) *bin = (int)s;          // one CTA per tile: plain store, the buffer need not be zeroed
         else if (s) atomicAdd(bin, (int)s);
     }
     if (want_gray) {
@@ -300,11 +300,12 @@ k_build_lut_rows(const int32_t *__restrict__ hist, int grid, int clip, float lut
     }
 }
 
-// per frame: flag = (max - min < thresh)  (pipeline.py:24-30)
-__global__ void k_gate_flags(const int32_t *__restrict__ gray_minmax, int n, float thresh, int32_t *__restrict__ flags)
+// per frame: flag = (max - min < thresh)  (pipeline.py:24-30); thresh is ceil() of the configured float, so the integer
+// comparison decides exactly like the reference's int-against-double comparison
+__global__ void k_gate_flags(const int32_t *__restrict__ gray_minmax, int n, int thresh, int32_t *__restrict__ flags)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flags[i] = ((float)(gray_minmax[2 * i + 1] - gray_minmax[2 * i]) < thresh) ? 1 : 0;
+    if (i < n) flags[i] = (gray_minmax[2 * i + 1] - gray_minmax[2 * i] < thresh) ? 1 : 0;
 }
 
 __global__ void k_init_minmax(int32_t *mm, int n)

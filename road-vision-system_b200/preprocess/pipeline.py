@@ -10,7 +10,7 @@ from typing import Any, Dict
 
 import numpy as np
 
-from .._native import Params, default_context
+from .._native import DeviceArray, Params, default_context
 from .base import as_bgr_u8
 from .ops import CLAHEDehaze, MedianDerain
 from .ops import clahe_dehaze as _clahe
@@ -23,7 +23,11 @@ def _is_cuda_tensor(x):
 
 
 class PreprocessPipeline:
-    def __init__(self, config: Dict[str, Any]):
+    def __init__(self, config: Dict[str, Any], context=None):
+        """`config`: the reference's `preprocess:` dict (pipeline.py:13-22).  `context` (new, optional): the rvb200.Context
+        this pipeline runs on -- give every camera stream / worker thread its own (a context is not thread-safe);
+        without it the process-wide default context of `config["device"]` is used."""
+        self._context = context
         self.enabled = bool(config.get("enabled", True))
         self.chain_cfg = config.get("chain", []) or []
         self.auto_gate_cfg = config.get("auto_gate", {}) or {}
@@ -37,7 +41,7 @@ class PreprocessPipeline:
 
     # -- helpers -------------------------------------------------------------------------
     def _ctx(self):
-        return default_context(self.device)
+        return self._context if self._context is not None else default_context(self.device)
 
     def _gate(self):
         enable = bool(self.auto_gate_cfg.get("enable_low_contrast_gate", False))
@@ -74,11 +78,19 @@ class PreprocessPipeline:
     def __call__(self, image: np.ndarray, ts: float = None) -> np.ndarray:
         if not self.enabled or not self.ops:
             return image
+        segs = self._segments()
         if self._gate()[0]:
+            if len(segs) == 1 and isinstance(segs[0], Params):
+                # one fused pass: the gate's gray span comes out of the histogram pass of the same upload
+                seg = segs[0]
+                seg.gate_enable, seg.gate_thresh = 1, self._gate()[1]
+                flag = np.ones(1, np.int32)
+                out = self._ctx().chain(as_bgr_u8(image)[None], seg, processed=flag)[0]
+                return out if flag[0] else image          # skipped: the input object itself, as pipeline.py:39-40
             if not self._low_contrast(image):
                 return image
         out = image
-        for seg in self._segments():
+        for seg in segs:
             if isinstance(seg, Params):
                 out = self._ctx().chain(as_bgr_u8(out)[None], seg)[0]
             else:
@@ -91,10 +103,16 @@ class PreprocessPipeline:
 
         `frames` / `out` may be pinned arrays from `Context.pinned_empty` (fastest: H2D, kernels
         and D2H of consecutive chunks overlap).  Frames the low-contrast gate skips are copied
-        through unchanged.
+        through unchanged.  `out="device"` keeps the result on the GPU (a `DeviceArray`, usable from torch / cupy through
+        `__cuda_array_interface__`): nothing is copied back, which is what a detector on the same GPU wants
+        (main_preview.py:99).
         """
         if _is_cuda_tensor(frames):
             return self._process_batch_device(frames, out)
+        if isinstance(out, str):
+            if out != "device":
+                raise ValueError('out must be an array, None or "device"')
+            return self._process_batch_keep(frames)
         if not isinstance(frames, np.ndarray) or frames.ndim != 4 or frames.shape[3] != 3 or frames.dtype != np.uint8:
             raise ValueError("frames must be a (B,H,W,3) uint8 numpy array (or a torch CUDA uint8 tensor of that shape)")
         if not self.enabled or not self.ops:
@@ -132,17 +150,42 @@ class PreprocessPipeline:
                     cur = out
         return cur
 
+    def _process_batch_keep(self, frames):
+        """Host frames in, result left on the GPU (no D2H at all)."""
+        if not isinstance(frames, np.ndarray) or frames.ndim != 4 or frames.shape[3] != 3 or frames.dtype != np.uint8:
+            raise ValueError("frames must be a (B,H,W,3) uint8 numpy array")
+        ctx = self._ctx()
+        frames = np.ascontiguousarray(frames)
+        segs = self._segments() if (self.enabled and self.ops) else []
+        if not segs or self._gate()[0] or not all(isinstance(sg, Params) for sg in segs):
+            # identity, gated or foreign operators: compute on the host path, then upload
+            res = self.process_batch(frames)
+            dev = DeviceArray(ctx, res.shape)
+            ctx._ck(ctx._lib.rv_memcpy(ctx._h, dev.ptr, np.ascontiguousarray(res).ctypes.data, dev.nbytes, 0))
+            return dev
+        cur = frames
+        for sg in segs:
+            dst = DeviceArray(ctx, frames.shape)
+            ctx.submit_io(cur, sg, shape=frames.shape[:3], out=dst)
+            ctx.wait()
+            cur = dst
+        return cur
+
     def _process_batch_device(self, frames, out=None):
         """Device-resident batch: a contiguous torch CUDA uint8 tensor (B,H,W,3) in, a tensor of the same kind out.
         Work is enqueued on torch's current stream (no host synchronisation): use the result with torch as usual."""
         import torch
         if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3 or not frames.is_contiguous():
             raise ValueError("frames must be a contiguous (B,H,W,3) uint8 CUDA tensor")
+        if out is not None and not (_is_cuda_tensor(out) and out.dtype == torch.uint8 and tuple(out.shape) == tuple(frames.shape)
+                                    and out.device == frames.device and out.is_contiguous()):
+            raise ValueError("out must be a contiguous uint8 CUDA tensor of the input's shape on the input's device")
         if not self.enabled or not self.ops:
             return frames if out is None else out.copy_(frames)
         if self._gate()[0]:
             raise ValueError("the low-contrast gate is not supported for device-resident batches; use numpy frames")
-        ctx = default_context(frames.device.index)
+        ctx = self._context if (self._context is not None and self._context.device == frames.device.index) \
+            else default_context(frames.device.index)
         b, h, w, _ = frames.shape
         segs = self._segments()
         if not all(isinstance(sg, Params) for sg in segs):
@@ -160,8 +203,13 @@ class PreprocessPipeline:
         return cur
 
     # -- new: chain fused with the detector-input stage ------------------------
-    def process_batch_to_tensor(self, frames: np.ndarray, size: int = 640, pad_value: int = 114, want_frames: bool = False):
+    def process_batch_to_tensor(self, frames: np.ndarray, size: int = 640, pad_value: int = 114, want_frames: bool = False,
+                                out=None):
         """(B,H,W,3) uint8 -> ((B,3,size,size) float16 network input, processed frames or None).
+
+        `out`: optional (B,3,size,size) float16 array for the tensor (pinned, from `Context.pinned_empty(shape, np.float16)`, for
+        the overlapped H2D / kernels / D2H pipeline), or "device" to leave the tensor on the GPU (a `DeviceArray`): with pinned
+        `frames` the only PCIe traffic is then the upload of the frames.
 
         The tensor is what the detector stage builds from `proc` right after the chain (main_preview.py:99 ->
         yolo_ultralytics.py:28-35: letterbox, BGR->RGB, HWC->CHW, /255, half).  When the chain is the stock
@@ -172,7 +220,29 @@ class PreprocessPipeline:
             raise ValueError("frames must be a (B,H,W,3) uint8 numpy array")
         ctx = self._ctx()
         segs = self._segments() if (self.enabled and self.ops) else []
+        keep = isinstance(out, str)
+        if keep and out != "device":
+            raise ValueError('out must be an array, None or "device"')
+        if out is not None and not keep and (out.shape != (frames.shape[0], 3, size, size) or out.dtype != np.float16
+                                             or not out.flags.c_contiguous):
+            raise ValueError("out must be a C-contiguous (B,3,size,size) float16 array")
         if self._gate()[0] or len(segs) != 1 or not isinstance(segs[0], Params):
             proc = self.process_batch(frames)
-            return ctx.letterbox_f16(proc, size, pad_value), (proc if want_frames else None)
-        return ctx.chain_letterbox(frames, segs[0], size, pad_value, want_full=want_frames)
+            t = ctx.letterbox_f16(proc, size, pad_value)
+            if keep:
+                dev = DeviceArray(ctx, t.shape, np.float16)
+                ctx._ck(ctx._lib.rv_memcpy(ctx._h, dev.ptr, t.ctypes.data, dev.nbytes, 0))
+                t = dev
+            elif out is not None:
+                np.copyto(out, t)
+                t = out
+            return t, (proc if want_frames else None)
+        if keep:
+            frames = np.ascontiguousarray(frames)
+            dev = DeviceArray(ctx, (frames.shape[0], 3, size, size), np.float16)
+            full = ctx._pooled_pinned(frames.shape) if (want_frames and frames.nbytes <= (64 << 20)) else \
+                (np.empty_like(frames) if want_frames else None)
+            ctx.submit_io(frames, segs[0], out=full, tensor=dev, size=size, pad_value=pad_value)
+            ctx.wait()
+            return dev, full
+        return ctx.chain_letterbox(frames, segs[0], size, pad_value, want_full=want_frames, out=out)

@@ -371,3 +371,184 @@ def test_c_abi_from_plain_c(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "mismatches 0" in r.stdout
+
+
+# ------------------------------------------------------------------ round 2: streams, limits, mixed host/device ends
+def test_two_caller_streams_share_one_context(ctx):
+    """two batches enqueued on different caller streams through one context use the same workspace set; the
+    context orders them with events, so neither overwrites the other's histograms / quad tables mid-use."""
+    torch = pytest.importorskip("torch")
+    import rvb200
+    from rvb200 import synth
+    a = synth.frame_pool(360, 640, 6, base_seed=200)
+    b = np.random.RandomState(5).randint(0, 256, (6, 360, 640, 3)).astype(np.uint8)
+    pa, pb = rvb200.Params.make("YCrCb", 2.0, 8, 5), rvb200.Params.make("LAB", 3.0, 4, 3)
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    oa, ob = torch.empty_like(da), torch.empty_like(db)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(4):                                           # several rounds back to back, no host sync in between
+        ctx.submit_device(da.data_ptr(), oa.data_ptr(), 6, 360, 640, pa, stream=s1.cuda_stream)
+        ctx.submit_device(db.data_ptr(), ob.data_ptr(), 6, 360, 640, pb, stream=s2.cuda_stream)
+    span = ctx.gray_span(a[:2])                                  # a stage call on the context's own stream in between
+    torch.cuda.synchronize()
+    ra, rb = oa.cpu().numpy(), ob.cpu().numpy()
+    for i in range(6):
+        assert np.array_equal(ra[i], O.chain(a[i], O.SPACE_YCRCB, 2.0, 8, 5)), i
+        assert np.array_equal(rb[i], O.chain(b[i], O.SPACE_LAB, 3.0, 4, 3)), i
+    assert [int(v) for v in span] == [O.gray_span(a[0]), O.gray_span(a[1])]
+
+
+def test_large_tile_grids(ctx):
+    """tile_grid 32 (per-quad LUT kernel, grids > 16) and the documented maximum 256 (65,536 tiles on gridDim.x)."""
+    import rvb200
+    rng = np.random.RandomState(12)
+    img = rng.randint(0, 256, (200, 333, 3)).astype(np.uint8)
+    for grid in (17, 32):
+        pl = O.luma(img, O.SPACE_YCRCB)
+        hist = O.clahe_hist(pl, grid)
+        assert np.array_equal(ctx.luma_hist(img[None], "YCrCb", grid, want_luma=False)[0][0], hist), grid
+        for clip in (0.0, 2.0, 40.0):
+            assert np.array_equal(ctx.build_lut(hist[None], 200, 333, grid, clip)[0], O.clahe_lut(hist, 200, 333, grid, clip)), (grid, clip)
+        for space, k in (("YCrCb", 5), ("LAB", 3)):
+            got = ctx.chain(img[None], rvb200.Params.make(space, 2.0, grid, k))[0]
+            assert np.array_equal(got, O.chain(img, ospace(space), 2.0, grid, k)), (grid, space)
+    small = rng.randint(0, 256, (70, 90, 3)).astype(np.uint8)
+    got = ctx.chain(small[None], rvb200.Params.make("YCrCb", 2.0, 256, 3))[0]
+    assert np.array_equal(got, O.chain(small, O.SPACE_YCRCB, 2.0, 256, 3))
+
+
+def test_many_tiny_frames_one_call(ctx):
+    """A batch larger than one launch's gridDim.z budget goes out in several launches (host and device paths)."""
+    torch = pytest.importorskip("torch")
+    import rvb200
+    n = 33000
+    frames = np.random.RandomState(8).randint(0, 256, (n, 4, 5, 3)).astype(np.uint8)
+    p = rvb200.Params.make("YCrCb", 2.0, 2, 3)
+    got = ctx.chain(frames, p)
+    d = torch.from_numpy(frames).cuda()
+    o = torch.empty_like(d)
+    ctx.chain_device(d.data_ptr(), o.data_ptr(), n, 4, 5, p)
+    assert np.array_equal(o.cpu().numpy(), got)
+    ctx.set_option("group_frames", 40000)                        # one group: every kernel of the chain splits its launch
+    try:
+        o.zero_()
+        ctx.chain_device(d.data_ptr(), o.data_ptr(), n, 4, 5, p)
+    finally:
+        ctx.set_option("group_frames", 0)
+    assert np.array_equal(o.cpu().numpy(), got)
+    for i in (0, 1, 32767, 32768, n - 1):
+        assert np.array_equal(got[i], O.chain(frames[i], O.SPACE_YCRCB, 2.0, 2, 3)), i
+    assert np.array_equal(ctx.gray_span(frames)[[0, 32768, n - 1]],
+                          [O.gray_span(frames[0]), O.gray_span(frames[32768]), O.gray_span(frames[n - 1])])
+
+
+def test_gate_threshold_boundary_is_decided_in_integers(ctx):
+    """thresholds that binary32 cannot represent must give the same decision in the fused batch path, the per-frame
+    path and the reference (int span against a Python float)."""
+    import rvb200
+    f = np.full((48, 64, 3), 100, np.uint8)
+    f[0, 0] = (120, 120, 120)                                   # gray span exactly 20
+    assert O.gray_span(f) == 20
+    for thresh, processed in ((20.0000001, True), (20.0, False), (19.9999999, False), (21, True), (0.0, False), (-3.0, False)):
+        cfg = {"chain": [{"name": "CLAHEDehaze"}, {"name": "MedianDerain"}],
+               "auto_gate": {"enable_low_contrast_gate": True, "contrast_thresh": thresh}}
+        pl = rvb200.PreprocessPipeline(cfg)
+        assert (20 < thresh) == processed
+        one = pl(f)
+        assert (one is not f) == processed, thresh
+        got = pl.process_batch(np.stack([f, f]))
+        want = O.chain(f, O.SPACE_YCRCB, 2.0, 8, 3) if processed else f
+        assert np.array_equal(got[0], want) and np.array_equal(got[1], want), thresh
+        if processed:
+            assert np.array_equal(one, want)
+
+
+def test_overlapping_buffers_are_rejected(ctx):
+    torch = pytest.importorskip("torch")
+    import rvb200
+    d = torch.zeros(3 * 32 * 32 * 3 + 64, dtype=torch.uint8, device="cuda")
+    p = rvb200.Params.make()
+    with pytest.raises(ValueError):
+        ctx.chain_device(d.data_ptr(), d.data_ptr() + 96, 2, 32, 32, p)          # partial overlap, one row down
+    pl = rvb200.PreprocessPipeline({"chain": [{"name": "MedianDerain"}]})
+    x = torch.zeros((2, 32, 32, 3), dtype=torch.uint8, device="cuda")
+    for bad in (torch.zeros((2, 32, 32, 3), dtype=torch.float16, device="cuda"), torch.zeros((2, 32, 31, 3), dtype=torch.uint8, device="cuda"),
+                torch.zeros((2, 32, 64, 3), dtype=torch.uint8, device="cuda")[:, :, ::2]):
+        with pytest.raises(ValueError):
+            pl.process_batch(x, out=bad)
+
+
+def test_results_that_stay_on_the_gpu(ctx):
+    """process_batch(out="device") and process_batch_to_tensor(out="device" | pinned): same bytes as the host path; the
+    device results are usable from torch through __cuda_array_interface__."""
+    torch = pytest.importorskip("torch")
+    import rvb200
+    from rvb200 import synth
+    frames = synth.frame_pool(1080, 1920, 7, base_seed=300)
+    cfg = {"chain": [{"name": "CLAHEDehaze", "params": {"space": "YCrCb"}}, {"name": "MedianDerain", "params": {"ksize": 5}}]}
+    pl = rvb200.PreprocessPipeline(cfg)
+    want = pl.process_batch(frames)
+    for i in (0, 6):
+        assert np.array_equal(want[i], O.chain(frames[i], O.SPACE_YCRCB, 2.0, 8, 5))
+    pin = ctx.pinned_empty(frames.shape)
+    pin[:] = frames
+    ctx.set_option("chunk_frames", 2)                            # several pipeline chunks, last one partial
+    try:
+        dev = pl.process_batch(pin, out="device")
+        assert isinstance(dev, rvb200.DeviceArray) and dev.shape == frames.shape
+        t = torch.as_tensor(dev, device="cuda")
+        assert t.data_ptr() == dev.ptr and np.array_equal(t.cpu().numpy(), want)
+        # detector tensor: pageable, pinned and device outputs, fused (1080p -> 640) path
+        t0, none = pl.process_batch_to_tensor(frames)
+        assert none is None
+        for i in (0, 6):
+            assert np.array_equal(t0[i].view(np.uint16), O.letterbox_f16(want[i], 640).view(np.uint16)), i
+        pt = ctx.pinned_empty((7, 3, 640, 640), np.float16)
+        t1, full = pl.process_batch_to_tensor(pin, out=pt, want_frames=True)
+        assert t1 is pt and np.array_equal(pt.view(np.uint16), t0.view(np.uint16)) and np.array_equal(full, want)
+        t2, _ = pl.process_batch_to_tensor(pin, out="device")
+        assert np.array_equal(t2.numpy().view(np.uint16), t0.view(np.uint16))
+        # unfused geometry (ragged size) through the same pipeline
+        rag = np.ascontiguousarray(frames[:3, :1079, :1917])
+        r0, _ = pl.process_batch_to_tensor(rag)
+        r2, rf = pl.process_batch_to_tensor(rag, out="device", want_frames=True)
+        assert np.array_equal(r2.numpy().view(np.uint16), r0.view(np.uint16))
+        for i in range(3):
+            proc = O.chain(rag[i], O.SPACE_YCRCB, 2.0, 8, 5)
+            assert np.array_equal(rf[i], proc)
+            assert np.array_equal(r0[i].view(np.uint16), O.letterbox_f16(proc, 640).view(np.uint16)), i
+    finally:
+        ctx.set_option("chunk_frames", 0)
+
+
+def test_batch_feeder_pinned_ring_to_process_batch(ctx):
+    """capture -> BatchFeeder(pinned ring) -> process_batch equals the per-frame oracle; per-frame capture
+    timestamps (capture.py:20) are monotonic; the last batch is partial."""
+    import rvb200
+    from rvb200 import synth
+    from rvb200.io_video.capture import SyntheticReader
+    h, w = 270, 480
+    pool = synth.frame_pool(h, w, 5, base_seed=400)
+    nframes, batch = 23, 8
+    pctx = rvb200.Context(0)                                     # the stream's own context, bound to its pipeline
+    pl = rvb200.PreprocessPipeline({"chain": [{"name": "CLAHEDehaze", "params": {"space": "LAB"}}, {"name": "MedianDerain"}]},
+                                   context=pctx)
+    assert pl._ctx() is pctx
+    vs = rvb200.VideoSource(reader=SyntheticReader(list(pool), limit=nframes))
+    feeder = rvb200.BatchFeeder(vs, batch=batch, shape=(h, w, 3), alloc=pctx.pinned_empty, depth=3)
+    out = pctx.pinned_empty((batch, h, w, 3))
+    want = [O.chain(f, O.SPACE_LAB, 2.0, 8, 3) for f in pool]
+    seen, counts, ts_all = 0, [], []
+    for b in feeder:
+        assert pctx.mem_kind(b.frames) == rvb200._native.MEM_PINNED
+        res = pl.process_batch(b.frames, out=out[:b.count])
+        for i in range(b.count):
+            assert np.array_equal(res[i], want[(seen + i) % len(pool)]), (seen, i)
+        ts_all.extend(b.ts)
+        counts.append(b.count)
+        seen += b.count
+        feeder.release(b)
+    assert seen == nframes and counts == [8, 8, 7]
+    assert all(t > 0 for t in ts_all) and np.all(np.diff(ts_all) >= 0)
+    pctx.close()

@@ -1,6 +1,10 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (read here, no GPU needed): headline metrics + SASS instruction mix per phase.
-usage: tools/ncu_summary.py gpurun_out/prof_chain_TAG.ncu-rep [out.txt]"""
+usage: tools/ncu_summary.py gpurun_out/prof_chain_TAG.ncu-rep [out.txt] [--json profiles/final_k_chain.json]
+
+--json also writes the per-launch constants bench.py reports (DRAM bytes, executed warp instructions, duration) together with
+the hash of the kernel sources they were measured on (rvb200.kernel_source_hash()); bench.py and tests/test_host_logic.py
+refuse constants whose hash differs from the tree."""
 import collections
 import csv
 import io
@@ -24,12 +28,56 @@ def ncu(rep, page):
     return list(csv.reader(io.StringIO(out)))
 
 
+def write_json(path, rep, hdr, d):
+    import json
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import rvb200
+
+    def num(name):
+        return float(d[hdr.index(name)].replace(',', ''))
+    unit = {h: u for h, u in zip(hdr, UNITS)}
+
+    def to_bytes(name):
+        u = unit[name].lower()
+        return num(name) * {'byte': 1, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9}[u]
+
+    def to_us(name):
+        u = unit[name].lower()
+        return num(name) * {'ns': 1e-3, 'us': 1, 'usecond': 1, 'nsecond': 1e-3, 'ms': 1e3, 'msecond': 1e3}[u]
+    j = {"kernel": d[hdr.index('Kernel Name')], "capture": os.path.basename(rep), "source_hash": rvb200.kernel_source_hash(),
+         "grid": d[hdr.index('Grid Size')] if 'Grid Size' in hdr else None,
+         "dram_bytes_read": to_bytes('dram__bytes_read.sum'), "dram_bytes_write": to_bytes('dram__bytes_write.sum'),
+         "warp_instructions": num('smsp__inst_executed.sum'), "duration_us_under_ncu": to_us('gpu__time_duration.sum'),
+         "issue_active_pct": num('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+         "pipe_alu_pct": num('sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active'),
+         "pipe_fma_pct": num('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'),
+         "shared_wavefronts": num('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum'),
+         "shared_bank_conflicts": num('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum'),
+         "note": "one launch over 64 x 1080p frames; ncu --set full --clock-control none (cold cache, serialised)"}
+    with open(path, 'w') as fh:
+        json.dump(j, fh, indent=1)
+        fh.write("\n")
+
+
+UNITS = []
+
+
 def main():
-    rep = sys.argv[1]
-    out = open(sys.argv[2], 'w') if len(sys.argv) > 2 else sys.stdout
+    args = list(sys.argv[1:])
+    jpath = None
+    if '--json' in args:
+        i = args.index('--json')
+        jpath = args[i + 1]
+        del args[i:i + 2]
+    rep = args[0]
+    out = open(args[1], 'w') if len(args) > 1 else sys.stdout
     rows = ncu(rep, 'raw')
     hdr, units, data = rows[0], rows[1], rows[2:]
     d = data[0]
+    UNITS[:] = units
+    if jpath:
+        write_json(jpath, rep, hdr, d)
     print(f"# {rep}\nkernel: {d[hdr.index('Kernel Name')]}", file=out)
     for w in WANT:
         if w in hdr:
