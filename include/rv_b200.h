@@ -91,7 +91,9 @@ const char *rv_last_error(const rv_ctx *ctx);
  * ahead; measured 0.8 % slower on B200, the staging wait is already hidden by the co-resident CTAs);
  * "overlap_groups" (default 0 = off: device batches cut into this many groups so that the histogram/LUT pass of
  * the next group runs on a high-priority side stream under the current group's k_chain; measured 1-6 % slower on
- * B200 because k_chain leaves no SM resources for co-resident CTAs). */
+ * B200 because k_chain leaves no SM resources for co-resident CTAs);
+ * "frame_graphs" (default 1: single-frame host calls -- rv_chain_u8 with n = 1 and contiguous rows, i.e. the per-frame plugin
+ * contract -- replay one captured CUDA graph per (shape, parameters) between the two copies; 0 = direct launches). */
 int rv_set_option(rv_ctx *ctx, const char *name, long value);
 /* kernels launched by this context since creation (for bench accounting) */
 long rv_launch_count(const rv_ctx *ctx);
@@ -104,6 +106,10 @@ int rv_kernel_time_reset(rv_ctx *ctx);
 /* pinned host memory for the batched entry */
 int rv_alloc_pinned(rv_ctx *ctx, size_t bytes, void **out);
 int rv_free_pinned(rv_ctx *ctx, void *p);
+/* page-lock memory the caller owns (e.g. a capture library's frame buffers, or huge-page backed memory) so that copies from /
+ * to it are plain DMA; unregister before freeing it */
+int rv_host_register(rv_ctx *ctx, void *p, size_t bytes);
+int rv_host_unregister(rv_ctx *ctx, void *p);
 /* device memory helpers (so that Python callers do not need torch/cupy) */
 int rv_alloc_device(rv_ctx *ctx, size_t bytes, void **out);
 int rv_free_device(rv_ctx *ctx, void *p);

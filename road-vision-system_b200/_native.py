@@ -51,10 +51,8 @@ class DeviceArray:
     def __init__(self, ctx, shape, dtype=np.uint8):
         self.shape, self.dtype = tuple(int(v) for v in shape), np.dtype(dtype)
         self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
-        p = C.c_void_p()
-        ctx._ck(ctx._lib.rv_alloc_device(ctx._h, max(self.nbytes, 1), C.byref(p)))
-        self.ptr, self.ctx = p.value, ctx
-        self._finalizer = weakref.finalize(self, ctx._lib.rv_free_device, ctx._h, C.c_void_p(p.value))
+        self.ptr, self.ctx = ctx._device_block(max(self.nbytes, 1)), ctx
+        self._finalizer = weakref.finalize(self, ctx._device_block_done, self.ptr, max(self.nbytes, 1))
 
     @property
     def __cuda_array_interface__(self):
@@ -115,6 +113,8 @@ EXPORTS = {
     "rv_launch_count": (C.c_long, [C.c_void_p]),
     "rv_alloc_pinned": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "rv_free_pinned": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rv_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "rv_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rv_alloc_device": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "rv_free_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rv_memcpy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
@@ -172,6 +172,25 @@ def _check_frames(frames):
         raise ValueError("empty frame")
 
 
+class _Lease(np.ndarray):
+    """Owner of one hand-out of a pooled page-locked block (see Context._pooled_pinned); users only ever see plain ndarray
+    views whose `.base` is this object."""
+    _home = None
+
+    def __del__(self):
+        home = self._home
+        if home is not None:
+            ctx, free, blk, keep = home
+            if len(free) < keep:
+                free.append(blk)
+            else:
+                ctx._pinned.pop(blk[0], None)
+                try:
+                    ctx._lib.rv_free_pinned(ctx._h, C.c_void_p(blk[0]))
+                except Exception:          # interpreter shutdown
+                    pass
+
+
 class Context:
     """One rv_ctx: a CUDA device, its streams and workspaces. Not thread-safe."""
 
@@ -185,6 +204,7 @@ class Context:
         self.device = int(device)
         self._pinned = {}          # base address -> nbytes
         self._pin_pool = {}        # nbytes -> [free page-locked blocks] (results of per-frame calls)
+        self._dev_pool = {}        # nbytes -> [free device blocks] (results that stay on the GPU)
         self._finalizer = weakref.finalize(self, self._lib.rv_destroy, h)
 
     # -- plumbing ------------------------------------------------------------------------
@@ -225,29 +245,47 @@ class Context:
     def _pooled_pinned(self, shape, dtype=np.uint8, keep=4):
         """Like pinned_empty, but the page-locked block goes back to a small per-size pool when the array dies, so a
         per-frame loop (`proc = pipeline(raw)`, main_preview.py:94) gets DMA-able result arrays without paying
-        cudaHostAlloc per call.  The array is the caller's: fresh, writable, never aliased while it is alive."""
-        nbytes = max(int(np.prod(shape)) * np.dtype(dtype).itemsize, 1)
-        free = self._pin_pool.setdefault(nbytes, [])
+        cudaHostAlloc per call.  The array is the caller's: fresh, writable, never aliased while it is alive.
+
+        Cheap by construction (about a microsecond): every block carries one persistent memoryview; a hand-out is an
+        `_Lease` (an ndarray subclass over that memoryview whose destructor returns the block) viewed as a plain ndarray,
+        so the block is recycled exactly when the last view of the array is gone."""
+        dt = np.dtype(dtype)
+        count = 1
+        for v in shape:
+            count *= int(v)
+        nbytes = max(count * dt.itemsize, 1)
+        free = self._pin_pool.get(nbytes)
+        if free is None:
+            free = self._pin_pool[nbytes] = []
         if free:
-            addr = free.pop()
+            blk = free.pop()
         else:
             p = C.c_void_p()
             self._ck(self._lib.rv_alloc_pinned(self._h, nbytes, C.byref(p)))
-            addr = p.value
-            self._pinned[addr] = nbytes
-        buf = (C.c_uint8 * nbytes).from_address(addr)
-        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        owner = self
+            self._pinned[p.value] = nbytes
+            blk = (p.value, memoryview((C.c_uint8 * nbytes).from_address(p.value)).cast("B"))
+        lease = np.ndarray.__new__(_Lease, shape, dt, blk[1])
+        lease._home = (self, free, blk, keep)
+        self._last_lease_addr = blk[0]
+        return lease.view(np.ndarray)
 
-        def _recycle(addr=addr, nbytes=nbytes):
-            pool = owner._pin_pool.setdefault(nbytes, [])
-            if len(pool) < keep:
-                pool.append(addr)
-            else:
-                owner._pinned.pop(addr, None)
-                owner._lib.rv_free_pinned(owner._h, C.c_void_p(addr))
-        weakref.finalize(buf, _recycle)
-        return arr
+    def _device_block(self, nbytes):
+        """Device memory for a DeviceArray; blocks are recycled per size (cudaMalloc / cudaFree cost milliseconds and
+        synchronise the device, which a per-batch allocation must not pay)."""
+        free = self._dev_pool.setdefault(nbytes, [])
+        if free:
+            return free.pop()
+        p = C.c_void_p()
+        self._ck(self._lib.rv_alloc_device(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def _device_block_done(self, ptr, nbytes, keep=3):
+        free = self._dev_pool.setdefault(nbytes, [])
+        if len(free) < keep:
+            free.append(ptr)
+        else:
+            self._lib.rv_free_device(self._h, C.c_void_p(ptr))
 
     def mem_kind(self, arr):
         a = arr.ctypes.data
@@ -263,15 +301,26 @@ class Context:
         if not frames.flags.c_contiguous:
             frames = np.ascontiguousarray(frames)
         n, h, w, _ = frames.shape
+        out_addr = None
         if out is None:
             # small results (the per-frame contract) land in recycled page-locked memory: the D2H copy is a plain DMA
-            out = self._pooled_pinned(frames.shape) if frames.nbytes <= (64 << 20) else np.empty_like(frames)
+            if frames.nbytes <= (64 << 20):
+                out = self._pooled_pinned(frames.shape)
+                out_addr = self._last_lease_addr
+            else:
+                out = np.empty_like(frames)
         elif out.shape != frames.shape or out.dtype != np.uint8 or not out.flags.c_contiguous:
             raise ValueError("out must be a C-contiguous uint8 array of the input's shape")
-        kind = MEM_PINNED if (self.mem_kind(frames) == MEM_PINNED and self.mem_kind(out) == MEM_PINNED) else MEM_HOST
+        if out_addr is None:
+            out_addr = out.ctypes.data
+        if n == 1:
+            kind = MEM_HOST
+        else:
+            kind = MEM_PINNED if (self.mem_kind(frames) == MEM_PINNED and self.mem_kind(out) == MEM_PINNED) else MEM_HOST
         pp = processed.ctypes.data_as(_i32p) if processed is not None else None
-        self._ck(self._lib.rv_chain_u8(self._h, frames.ctypes.data, out.ctypes.data, n, h, w, 3 * w, 3 * w,
-                                       C.byref(params), kind, pp, None))
+        rc = self._lib.rv_chain_u8(self._h, frames.ctypes.data, out_addr, n, h, w, 3 * w, 3 * w, C.byref(params), kind, pp, None)
+        if rc != 0:
+            self._ck(rc)
         return out
 
     def chain_device(self, in_ptr, out_ptr, n, h, w, params, in_pitch=None, out_pitch=None, stream=None):

@@ -25,6 +25,8 @@ using namespace rv;
 namespace {
 
 constexpr int NPIPE = 3;
+constexpr int NWS = NPIPE + 3;               // workspace sets: [0, NPIPE) host pipeline, NPIPE / NPIPE+1 device path, NPIPE+2 single-frame path
+constexpr int WS_FRAME = NPIPE + 2;
 
 struct Buf {
     void *p = nullptr;
@@ -59,20 +61,38 @@ struct LbTab {                              // cv2.resize tables of k_letterbox 
     cudaEvent_t ready = nullptr;
     cudaStream_t up = nullptr;
 };
-constexpr int MAX_TABS = 32;                // geometries cached per context before the cache is flushed
+constexpr int MAX_TABS = 32;
+constexpr int MAX_FRAME_GRAPHS = 16;
+                // geometries cached per context before the cache is flushed
 constexpr int MAX_FRAMES_PER_LAUNCH = 32768; // frames ride on gridDim.z / gridDim.y (limit 65535)
 
 }  // namespace
+
+// One instantiated CUDA graph per (frame shape, parameters) for the per-frame plugin contract `proc = pipeline(raw)`
+// (main_preview.py:94): histogram (+ gate) -> LUT -> k_chain (-> gate copy, flag read-back) replayed with one launch between
+// the H2D copy of the frame and the D2H copy of the result, which are issued around it because their host pointers change.
+struct FrameGraph {
+    int h = 0, w = 0;
+    rv_params p = {};
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    void *bufs[6] = {};                     // the device buffers the graph was captured on (a reallocation invalidates it)
+    long kernels = 0;                       // kernel nodes in the graph (launch accounting)
+};
 
 struct rv_ctx {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;          // main stream (device buffers, stage-level calls)
     cudaStream_t pipe[NPIPE] = {};          // H2D / compute / D2H pipeline for host buffers
-    Buf hist[NPIPE + 2], quads[NPIPE + 2], lut[NPIPE + 2], flags[NPIPE + 2], mm[NPIPE + 2];   // [NPIPE], [NPIPE+1]: device path
-    Buf din[NPIPE + 2], dout[NPIPE + 2];
+    Buf hist[NWS], quads[NWS], lut[NWS], flags[NWS], mm[NWS];
+    Buf din[NWS], dout[NWS];
     Buf dlb[NPIPE];                         // detector tensors of the host pipeline's chunks
-    WsSync wsync[NPIPE + 2];
+    WsSync wsync[NWS];
+    cudaStream_t fstream = nullptr;         // single-frame path (per-frame plugin contract): its own stream, workspace set and graphs
+    std::vector<struct FrameGraph> fgraphs;
+    int32_t *fflag = nullptr;               // page-locked: gate decision of the single-frame path
+    long frame_graphs = 1;                  // option "frame_graphs": 0 = the single-frame path launches directly (no CUDA graph)
     std::vector<ColTab> coltabs;
     std::vector<LbTab> lbtabs;
     cudaStream_t aux = nullptr;             // high-priority stream: histogram/LUT of the next group under the current k_chain
@@ -414,9 +434,19 @@ int launch_lut(rv_ctx *ctx, const int32_t *hist, const Geo &g, double clip_limit
 
 // A geometry table is uploaded on the stream that first needs it (page-locked host copy kept with the entry) and is read-only
 // afterwards; other streams wait for the upload event.  Nothing synchronises the device.
+void drop_frame_graphs(rv_ctx *ctx)
+{
+    for (FrameGraph &g : ctx->fgraphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+    }
+    ctx->fgraphs.clear();
+}
+
 int flush_tables(rv_ctx *ctx)
 {
     CK(cudaDeviceSynchronize());            // rare: more than MAX_TABS geometries seen by one context
+    drop_frame_graphs(ctx);                 // they reference the column records
     for (ColTab &t : ctx->coltabs) { cudaFree(t.dev); cudaFreeHost(t.host); cudaEventDestroy(t.ready); }
     for (LbTab &t : ctx->lbtabs) { cudaFree(t.dev); cudaFreeHost(t.host); cudaEventDestroy(t.ready); }
     ctx->coltabs.clear();
@@ -427,11 +457,12 @@ int flush_tables(rv_ctx *ctx)
 // Column records for k_chain (A.3 horizontal terms), built once per (W, tile width).  Record r describes
 // the four pixels 4*(r-1) .. 4*(r-1)+3 (clamped into the frame): xa, xa1 = 1 - xa, -2^23*xa, -2^23*xa1, quad column.
 // Every value is produced by single IEEE-754 binary32 operations, exactly as the kernel used to compute them.
-int get_colparams(rv_ctx *ctx, const Geo &g, cudaStream_t st, const float **out)
+int get_colparams(rv_ctx *ctx, const Geo &g, cudaStream_t st, const float **out, bool capturing = false)
 {
     for (ColTab &t : ctx->coltabs)
         if (t.w == g.W && t.tw == g.tw) {
-            if (t.up != st) CK(cudaStreamWaitEvent(st, t.ready, 0));
+            // (while capturing, the same stream has already waited for the upload in the direct run that precedes the capture)
+            if (t.up != st && !capturing) CK(cudaStreamWaitEvent(st, t.ready, 0));
             *out = t.dev;
             return RV_OK;
         }
@@ -470,14 +501,18 @@ struct LbFused {            // fused detector-input stage of one group (integer 
 
 int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs, uint8_t *dout, size_t opitch, size_t ofs,
               int n, int h, int w, const rv_params *p, cudaStream_t st, int32_t **flags_out, const LbFused *lb = nullptr,
-              cudaStream_t st_pre = nullptr, cudaEvent_t ev_pre = nullptr)
+              cudaStream_t st_pre = nullptr, cudaEvent_t ev_pre = nullptr, bool capturing = false)
 {
+    // capturing: `st` is in stream capture (single-frame graph): nothing may allocate, wait for or record outside events; the
+    // set WS_FRAME is only ever used on that one stream, so it needs no cross-stream ordering
     // st_pre (optional): histogram / LUT / gate flags run there and `st` waits for them before k_chain
     cudaStream_t sp = st_pre ? st_pre : st;
     // the previous user of this workspace set may have been on another stream (two caller streams, or a stage-level call)
     WsSync &wsy = ctx->wsync[ws];
-    if (wsy.used && wsy.last != sp) CK(cudaStreamWaitEvent(sp, wsy.ev, 0));
-    if (wsy.used && st != sp && wsy.last != st) CK(cudaStreamWaitEvent(st, wsy.ev, 0));
+    if (!capturing) {
+        if (wsy.used && wsy.last != sp) CK(cudaStreamWaitEvent(sp, wsy.ev, 0));
+        if (wsy.used && st != sp && wsy.last != st) CK(cudaStreamWaitEvent(st, wsy.ev, 0));
+    }
     const int gate_t = gate_thresh_int(p->gate_thresh);
     ChainArgs a;
     a.src = din; a.spitch = ipitch; a.sfstride = ifs;
@@ -524,7 +559,7 @@ int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs
             CK(cudaEventRecord(ev_pre, st_pre));
             CK(cudaStreamWaitEvent(st, ev_pre, 0));
         }
-        RV_TRY(get_colparams(ctx, g, st, &a.colp));
+        RV_TRY(get_colparams(ctx, g, st, &a.colp, capturing));
         RV_TRY(launch_chain(ctx, p->space == RV_SPACE_LAB ? 1 : 0, a, n, p->ksize, st));
     }
     if (a.flags) {
@@ -537,6 +572,7 @@ int run_group(rv_ctx *ctx, int ws, const uint8_t *din, size_t ipitch, size_t ifs
         if (flags_out) *flags_out = (int32_t *)ctx->flags[ws].p;
     }
     CK(cudaGetLastError());
+    if (capturing) return RV_OK;
     CK(cudaEventRecord(wsy.ev, st));        // (a caller that reads the flags afterwards records it again, see ws_release)
     wsy.last = st;
     wsy.used = true;
@@ -622,6 +658,7 @@ int wait_all(rv_ctx *ctx)
     for (int i = 0; i < NPIPE; ++i) CK(cudaStreamSynchronize(ctx->pipe[i]));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->aux));
+    if (ctx->fstream) CK(cudaStreamSynchronize(ctx->fstream));
     return RV_OK;
 }
 
@@ -843,6 +880,84 @@ int chain_pipe(rv_ctx *ctx, const PipeJob &j, int n, int h, int w, const rv_para
     return RV_OK;
 }
 
+// ---- the single-frame path: `proc = pipeline(raw)` (main_preview.py:94), one frame in flight, lowest latency --------------
+// Host rows are contiguous (pitch 3w).  H2D copy, one graph launch (or the direct launches), D2H copy, one synchronisation.
+int frame_kernels(rv_ctx *ctx, int h, int w, const rv_params *p, bool capturing)
+{
+    cudaStream_t st = ctx->fstream;
+    const size_t pitch = (size_t)3 * w, fs = pitch * h;
+    int32_t *flags = nullptr;
+    RV_TRY(run_group(ctx, WS_FRAME, (const uint8_t *)ctx->din[WS_FRAME].p, pitch, fs, (uint8_t *)ctx->dout[WS_FRAME].p, pitch, fs, 1, h, w, p,
+                     st, &flags, nullptr, nullptr, nullptr, capturing));
+    if (flags) CK(cudaMemcpyAsync(ctx->fflag, flags, 4, cudaMemcpyDeviceToHost, st));
+    return RV_OK;
+}
+
+void frame_bufs(rv_ctx *ctx, void *(&b)[6])
+{
+    b[0] = ctx->din[WS_FRAME].p; b[1] = ctx->dout[WS_FRAME].p; b[2] = ctx->hist[WS_FRAME].p;
+    b[3] = ctx->quads[WS_FRAME].p; b[4] = ctx->mm[WS_FRAME].p; b[5] = ctx->flags[WS_FRAME].p;
+}
+
+int chain_frame(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int h, int w, const rv_params *p, int32_t *processed)
+{
+    cudaStream_t st = ctx->fstream;
+    const size_t fb = (size_t)3 * w * h;
+    RV_TRY(ensure(ctx, ctx->din[WS_FRAME], fb));
+    RV_TRY(ensure(ctx, ctx->dout[WS_FRAME], fb));
+    CK(cudaMemcpyAsync(ctx->din[WS_FRAME].p, in, fb, cudaMemcpyHostToDevice, st));
+    *ctx->fflag = 1;
+    FrameGraph *fg = nullptr;
+    const bool use_graph = ctx->frame_graphs != 0 && ctx->kernel_timing == 0;
+    if (use_graph) {
+        void *cur[6];
+        frame_bufs(ctx, cur);
+        for (size_t i = 0; i < ctx->fgraphs.size(); ++i) {
+            FrameGraph &g = ctx->fgraphs[i];
+            if (g.h == h && g.w == w && memcmp(&g.p, p, sizeof *p) == 0) {
+                if (memcmp(g.bufs, cur, sizeof cur) == 0) { fg = &g; break; }
+                cudaGraphExecDestroy(g.exec);            // a workspace was reallocated since the capture: stale pointers
+                cudaGraphDestroy(g.graph);
+                ctx->fgraphs.erase(ctx->fgraphs.begin() + i);
+                break;
+            }
+        }
+    }
+    if (fg) {
+        CK(cudaGraphLaunch(fg->exec, st));
+        ctx->launches += fg->kernels;
+    } else {
+        // first frame of this (shape, parameters): direct launches (they size the workspaces and upload the tables) ...
+        RV_TRY(frame_kernels(ctx, h, w, p, false));
+    }
+    CK(cudaMemcpyAsync(out, ctx->dout[WS_FRAME].p, fb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (processed) *processed = *ctx->fflag;
+    if (!fg && use_graph) {
+        // ... then the same sequence is captured for the frames that follow (nothing allocates or waits any more)
+        if ((int)ctx->fgraphs.size() >= MAX_FRAME_GRAPHS) drop_frame_graphs(ctx);
+        FrameGraph g;
+        g.h = h; g.w = w; g.p = *p;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const long launches = ctx->launches;
+            const int rc = frame_kernels(ctx, h, w, p, true);
+            g.kernels = ctx->launches - launches;
+            ctx->launches = launches;                                   // captured, not launched
+            cudaError_t e = cudaStreamEndCapture(st, &g.graph);
+            if (rc == RV_OK && e == cudaSuccess && g.graph && cudaGraphInstantiate(&g.exec, g.graph, 0) == cudaSuccess) {
+                frame_bufs(ctx, g.bufs);
+                ctx->fgraphs.push_back(g);
+            } else {
+                if (g.graph) cudaGraphDestroy(g.graph);
+                (void)cudaGetLastError();                               // the direct path keeps working without a graph
+            }
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
+    return RV_OK;
+}
+
 int check_lb_args(rv_ctx *ctx, const void *tensor, int S, int pad_value)
 {
     if (!tensor || S < 1 || S > 8192 || pad_value < 0 || pad_value > 255) return fail(ctx, RV_ERR_ARG, "bad letterbox arguments");
@@ -897,6 +1012,8 @@ int rv_create(int device, rv_ctx **out)
             if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
         for (WsSync &w : ctx->wsync)
             if (cudaEventCreateWithFlags(&w.ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
+        if (cudaStreamCreateWithFlags(&ctx->fstream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RV_ERR_CUDA; }
+        if (cudaHostAlloc((void **)&ctx->fflag, 64, cudaHostAllocDefault) != cudaSuccess) { delete ctx; return RV_ERR_NOMEM; }
     }
     // LAB tables
     LabTabs *t = new (std::nothrow) LabTabs();
@@ -931,7 +1048,7 @@ void rv_destroy(rv_ctx *ctx)
     cudaDeviceSynchronize();
     Buf *sets[] = {ctx->hist, ctx->quads, ctx->lut, ctx->flags, ctx->mm, ctx->din, ctx->dout};
     for (Buf *set : sets)
-        for (int i = 0; i <= NPIPE + 1; ++i)
+        for (int i = 0; i < NWS; ++i)
             if (set[i].p) cudaFree(set[i].p);
     for (Buf &b : ctx->dlb)
         if (b.p) cudaFree(b.p);
@@ -941,6 +1058,9 @@ void rv_destroy(rv_ctx *ctx)
     for (LbTab &t : ctx->lbtabs) { cudaFree(t.dev); cudaFreeHost(t.host); cudaEventDestroy(t.ready); }
     for (WsSync &w : ctx->wsync)
         if (w.ev) cudaEventDestroy(w.ev);
+    drop_frame_graphs(ctx);
+    if (ctx->fstream) cudaStreamDestroy(ctx->fstream);
+    if (ctx->fflag) cudaFreeHost(ctx->fflag);
     for (const TimedLaunch &t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < NPIPE; ++i)
@@ -964,6 +1084,7 @@ int rv_set_option(rv_ctx *ctx, const char *name, long value)
     if (strcmp(name, "use_tma") == 0) { ctx->use_tma = value; return RV_OK; }
     if (strcmp(name, "prefetch_ctas") == 0) { ctx->prefetch_ctas_per_sm = value < 0 ? 0 : value; return RV_OK; }
     if (strcmp(name, "overlap_groups") == 0) { ctx->overlap_groups = value; return RV_OK; }
+    if (strcmp(name, "frame_graphs") == 0) { ctx->frame_graphs = value; return RV_OK; }
     return fail(ctx, RV_ERR_ARG, "unknown option '%s'", name);
 }
 
@@ -982,6 +1103,22 @@ int rv_free_pinned(rv_ctx *ctx, void *p)
 {
     if (!ctx) return RV_ERR_ARG;
     if (p) CK(cudaFreeHost(p));
+    return RV_OK;
+}
+
+int rv_host_register(rv_ctx *ctx, void *p, size_t bytes)
+{
+    if (!ctx || !p || bytes == 0) return RV_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) return fail(ctx, RV_ERR_CUDA, "cudaHostRegister(%zu): %s", bytes, cudaGetErrorString(e));
+    return RV_OK;
+}
+
+int rv_host_unregister(rv_ctx *ctx, void *p)
+{
+    if (!ctx || !p) return RV_ERR_ARG;
+    CK(cudaHostUnregister(p));
     return RV_OK;
 }
 
@@ -1125,6 +1262,8 @@ int rv_chain_u8(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int n, int h, int 
         CK(cudaStreamSynchronize(st));
         return RV_OK;
     }
+    if (n == 1 && in_pitch == (size_t)3 * w && out_pitch == (size_t)3 * w)
+        return chain_frame(ctx, in, out, h, w, p, processed);
     PipeJob j;
     j.in = in; j.in_kind = mem_kind; j.ipitch = in_pitch;
     j.out = out; j.out_kind = mem_kind; j.opitch = out_pitch;

@@ -41,7 +41,11 @@ class SyntheticReader:
 
 
 class VideoSource:
-    def __init__(self, source=0, width=1280, height=720, fps_request=30, backend="auto", reader=None):
+    def __init__(self, source=0, width=1280, height=720, fps_request=30, backend="auto", reader=None, pinned="auto"):
+        """Same constructor as the reference (capture.py:11-16).  New, optional: `reader` (any object with read() / release())
+        and `pinned`: a rvb200.Context (or "auto" = the process-wide default context when a GPU is usable, None / False = off).
+        With it, read() hands out frames that already live in page-locked memory (fresh, caller-owned arrays whose blocks
+        are recycled when they are garbage-collected), so `pipeline(raw)` uploads them with a plain DMA."""
         if reader is not None:
             self.cap = reader
         else:
@@ -50,9 +54,46 @@ class VideoSource:
             self.cap.set(cv2.CAP_PROP_FRAME_WIDTH, width)
             self.cap.set(cv2.CAP_PROP_FRAME_HEIGHT, height)
             self.cap.set(cv2.CAP_PROP_FPS, fps_request)
+        self._pin_ctx = None
+        self._shape = None
+        self._into = None              # does the reader's read() accept a destination array (cv2.VideoCapture does)?
+        if pinned == "auto":
+            try:
+                from .._native import default_context
+                self._pin_ctx = default_context()
+            except Exception:          # no GPU / library not built: frames stay in pageable memory (placement only)
+                self._pin_ctx = None
+        elif pinned:
+            self._pin_ctx = pinned
+
+    def _read_pinned(self):
+        buf = self._pin_ctx._pooled_pinned(self._shape, keep=8)
+        if self._into is not False:
+            try:
+                ok, img = self.cap.read(buf)
+                self._into = True
+            except TypeError:
+                self._into = False
+                ok, img = self.cap.read()
+        else:
+            ok, img = self.cap.read()
+        if not ok or img is None:
+            return ok, img
+        if img is buf:
+            return ok, img
+        if isinstance(img, np.ndarray) and img.shape == self._shape and img.dtype == np.uint8:
+            np.copyto(buf, img)
+            return ok, buf
+        self._shape = None             # geometry changed mid-stream: hand the frame out as it is
+        return ok, img
 
     def read(self) -> Frame:
-        ok, img = self.cap.read()
+        if self._pin_ctx is not None and self._shape is not None:
+            ok, img = self._read_pinned()
+        else:
+            ok, img = self.cap.read()
+            if ok and self._pin_ctx is not None and isinstance(img, np.ndarray) and img.dtype == np.uint8 and img.ndim == 3:
+                self._shape = img.shape        # from the next frame on, frames are captured into page-locked blocks
         return Frame(ok, img, time.time())
 
     def read_batch(self, n, out=None):

@@ -28,6 +28,7 @@ class PreprocessPipeline:
         this pipeline runs on -- give every camera stream / worker thread its own (a context is not thread-safe);
         without it the process-wide default context of `config["device"]` is used."""
         self._context = context
+        self._snap = None
         self.enabled = bool(config.get("enabled", True))
         self.chain_cfg = config.get("chain", []) or []
         self.auto_gate_cfg = config.get("auto_gate", {}) or {}
@@ -53,7 +54,25 @@ class PreprocessPipeline:
         return span < self._gate()[1]
 
     def _segments(self):
-        """Fold the op list into fused GPU passes: [(Params | op)]; params are re-read every call."""
+        """Fold the op list into fused GPU passes: [(Params | op)].  Params are re-read on every call, like the reference
+        (clahe_dehaze.py:14-17, median_derain.py:11-13: mutating `op.params` between frames takes effect); the folded result
+        is reused for as long as the op objects and their params dicts compare equal to the snapshot it was built from."""
+        snap = self._snap
+        ops = self.ops
+        if snap is not None and len(snap[0]) == len(ops):
+            for (op0, params0), op in zip(snap[0], ops):
+                if op0 is not op or params0 != op.params:
+                    break
+            else:
+                for sg in snap[1]:
+                    if isinstance(sg, Params):
+                        sg.gate_enable = 0
+                return snap[1]
+        segs = self._fold()
+        self._snap = ([(op, dict(op.params)) for op in ops], segs)
+        return segs
+
+    def _fold(self):
         segs, i = [], 0
         while i < len(self.ops):
             op = self.ops[i]
