@@ -187,6 +187,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             if (gy < 0 || gy >= g.H) continue;
             const uint8_t *rp = frame + (size_t)gy * a.spitch + bx0;
             uint32_t *ar = reinterpret_cast<uint32_t *>(A + ry * A_STRIDE);
+            RV_CHECK_IDX(ry * A_STRIDE + A_STRIDE - 1, S::a_bytes, "A (staging store)");
             if (full) {
                 const uint32_t *rw = reinterpret_cast<const uint32_t *>(rp);
                 const uint32_t v0 = __ldg(rw + lane), v1 = __ldg(rw + lane + 32), v2 = __ldg(rw + lane + 64);
@@ -245,6 +246,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
                 const int lq = i >> 6, v4 = i & 63;
                 const int dq = (lq * rcp) >> 8;
                 const int qy = qy_lo + dq, qx = qx_lo + lq - dq * nqx;
+                RV_CHECK_IDX(16 * i + 15, S::q_bytes, "Qs (quad table fill)");
                 reinterpret_cast<uint4 *>(Qs)[i] = __ldg(reinterpret_cast<const uint4 *>(qf + ((size_t)qy * (g.grid + 1) + qx) * 256) + v4);
             }
         }
@@ -259,6 +261,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             const float fl = floorf(tyf);
             const float ya = __fsub_rn(tyf, fl);
             const int qy = (int)fl + 1;
+            RV_CHECK_IDX(ry, BOX_H, "rowp");
             rowp[ry] = make_float4(ya, __fsub_rn(1.0f, ya), __int_as_float(q_smem ? (((qy - qy_lo) * nqx) << 8) : qy),
                                    __int_as_float((gy - (y0 - R)) * A_STRIDE));
         }
@@ -293,7 +296,9 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             ar = A + __float_as_int(rp.w);                 // staged row of the clamped image row
         }
         uint32_t px[4];                                    // (B, G, R, x) of each pixel in one word
+        RV_CHECK_IDX(ar - A, S::a_bytes - A_STRIDE + 1, "A (row base)");
         if (lane_inside) {
+            RV_CHECK_IDX((ar - A) + aoff + 12 * lane + 11, S::a_bytes, "A (packed pixel load)");
             const uint32_t *p = reinterpret_cast<const uint32_t *>(ar + aoff + 12 * lane);
             const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];
             px[0] = w0; px[1] = __funnelshift_r(w0, w1, 24); px[2] = __funnelshift_r(w1, w2, 16); px[3] = w2 >> 8;
@@ -308,6 +313,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             for (int j = 0; j < 4; ++j) {
                 const int cx = min(max(x0 - LPAD + 4 * lane + j, 0), g.W - 1);
                 const uint8_t *p = ar + aoff + 3 * (cx - (x0 - LPAD));
+                RV_CHECK_IDX(p - A, S::a_bytes - 2, "A (edge pixel load)");
                 Bv[j] = p[0]; Gv[j] = p[1]; Rv[j] = p[2];
                 px[j] = (uint32_t)Bv[j] | ((uint32_t)Gv[j] << 8) | ((uint32_t)Rv[j] << 16);
             }
@@ -339,6 +345,9 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
                 asm("ld.shared.u32 %0, [%1+2048];" : "=r"(eR) : "r"(yrow + 4u * (uint32_t)Rv[j]));
             }
             uint32_t q;
+            if constexpr (q_in_smem) RV_CHECK_IDX(qrow + qcol[j] + L, MAXQ * 256, "Qs (LUT quad load)");
+            if constexpr (MODE == 0) RV_CHECK_IDX(255 - L + Bv[j], 512, "ycc table (B - Y)");
+            if constexpr (MODE == 0) RV_CHECK_IDX(255 - L + Rv[j], 512, "ycc table (R - Y)");
             if constexpr (q_in_smem) q = Qs[qrow + qcol[j] + L];
             else q = __ldg(qglob + (((size_t)qrow * (g.grid + 1) + (qxl[j] + qx_lo)) << 8) + L);
             // 0x4B0000vv = 2^23 + vv ; fma(2^23 + v, w, -2^23 * w) == v * w rounded once (A.3: no FMA contraction
@@ -397,6 +406,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             int o[12];
             compute_row(ry, o);                      // all 32 lanes: compute_row votes across the warp (LAB inverse)
             if (lane >= 1 && lane <= 30) {
+                RV_CHECK_IDX(ry * O_STRIDE + 12 * (lane - 1) + 11, S::p_bytes, "O (K = 0 staging)");
                 uint32_t *op = reinterpret_cast<uint32_t *>(O + ry * O_STRIDE + 12 * (lane - 1));
                 op[0] = (uint32_t)o[0] | ((uint32_t)o[4] << 8) | ((uint32_t)o[8] << 16) | ((uint32_t)o[1] << 24);
                 op[1] = (uint32_t)o[5] | ((uint32_t)o[9] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[6] << 24);
@@ -417,6 +427,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
                 w.y = pack2(o0[4 * c + 1], o1[4 * c + 1]);
                 w.z = pack2(o0[4 * c + 2], o1[4 * c + 2]);
                 w.w = pack2(o0[4 * c + 3], o1[4 * c + 3]);
+                RV_CHECK_IDX(4 * ((c * NSLOT + s) * P_STRIDE + 4 * lane) + 15, S::p_bytes, "P (plane store)");
                 *reinterpret_cast<uint4 *>(P + (c * NSLOT + s) * P_STRIDE + 4 * lane) = w;
             }
             if (s < 2 * R) {       // rows [HALF, HALF+2R) are also the low half of slots [HALF, HALF+2R)
@@ -428,6 +439,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
                     w.y = pack2(o1[4 * c + 1], o0[4 * c + 1]);
                     w.z = pack2(o1[4 * c + 2], o0[4 * c + 2]);
                     w.w = pack2(o1[4 * c + 3], o0[4 * c + 3]);
+                    RV_CHECK_IDX(4 * ((c * NSLOT + s + HALF) * P_STRIDE + 4 * lane) + 15, S::p_bytes, "P (tail plane store)");
                     *reinterpret_cast<uint4 *>(P + (c * NSLOT + s + HALF) * P_STRIDE + 4 * lane) = w;
                 }
             }
@@ -464,6 +476,8 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             if (!live) continue;
             uint32_t v[NC][NR];
             const uint32_t *pc = P + (co * NSLOT + s) * P_STRIDE;
+            RV_CHECK_IDX(4 * ((pc - P) + (NR - 1) * P_STRIDE + M * mo + C0 + NC - 1) + 3, S::p_bytes, "P (two-row median load)");
+            RV_CHECK_IDX((pc - P) + M * mo + (C0 & ~1), S::p_bytes / 4, "P (two-row median first word)");
             if constexpr (M == 4) {
 #pragma unroll
                 for (int d = 0; d < NR; ++d) {
@@ -502,6 +516,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             for (int hrow = 0; hrow < 2; ++hrow) {
                 uint8_t *o0 = O + (s + hrow) * O_STRIDE + 3 * M * mo + co;
                 uint8_t *o1 = o0 + HALF * O_STRIDE;
+                RV_CHECK_IDX((o1 - O) + 3 * (M - 1), S::a_bytes, "O (two-row median store)");
 #pragma unroll
                 for (int j = 0; j < M; ++j) {
                     o0[3 * j] = (uint8_t)(out[hrow][j] & 255);
@@ -524,6 +539,8 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             uint32_t v[NC][K];
             const uint32_t *pc = P + (c * NSLOT + s) * P_STRIDE;
             constexpr int C0 = LPAD - R;                 // first needed plane word, relative to the group's first output
+            RV_CHECK_IDX(4 * ((pc - P) + (K - 1) * P_STRIDE + M * m + C0 + NC - 1) + 3, S::p_bytes, "P (median load)");
+            RV_CHECK_IDX((pc - P) + M * m + C0, S::p_bytes / 4, "P (median first word)");
             if constexpr (M == 4) {
                 // 16-byte loads of words 4m .. 4m+11 (conflict-free: 8 lanes x 16 B per phase)
 #pragma unroll
@@ -555,6 +572,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             median_net<K, NC, M>(v, out);
             uint8_t *o0 = O + s * O_STRIDE + 3 * M * m + c;
             uint8_t *o1 = o0 + HALF * O_STRIDE;
+            RV_CHECK_IDX((o1 - O) + 3 * (M - 1), S::a_bytes, "O (median store)");
 #pragma unroll
             for (int j = 0; j < M; ++j) {
                 o0[3 * j] = (uint8_t)(out[j] & 255);
@@ -578,6 +596,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             // full tile, 8-byte aligned rows (3*x0 = 360*bx): 45 double words per row, four rows per warp, fully unrolled
             uint8_t *dp = dframe + (size_t)(y0 + warp) * a.dpitch + 3 * (size_t)x0 + 8 * lane;
             const uint8_t *op = O + warp * O_STRIDE + 8 * lane;
+            RV_CHECK_IDX((TILE_H - CHAIN_WARPS + warp) * O_STRIDE + 8 * (lane < 13 ? lane + 32 : lane) + 7, (K > 0 ? S::a_bytes : S::p_bytes), "O (tile store)");
             const size_t dstep = (size_t)CHAIN_WARPS * a.dpitch;
 #pragma unroll
             for (int k = 0; k < TILE_H / CHAIN_WARPS; ++k) {
@@ -626,6 +645,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
                 const int ry = i / ncol, rx = i - ry * ncol;
                 const int dy = dy0 + ry, dx = dx0 + rx;
                 const uint8_t *p = O + (sc * dy + off - y0) * O_STRIDE + 3 * (sc * dx + off - x0);
+                RV_CHECK_IDX((p - O) + (even ? O_STRIDE + 3 : 0) + 2, TILE_H * O_STRIDE, "O (fused letterbox read)");
                 int v[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {

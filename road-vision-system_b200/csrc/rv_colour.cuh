@@ -75,17 +75,33 @@ __device__ __forceinline__ int lab_L_fast(const LabHistTabs *t, int B, int G, in
     return t->lq[(t->pm[0][R] + t->pm[1][G] + t->pm[2][B]) >> 12];
 }
 
+// Right shifts of the LAB fixed-point code.  RV_LAB_MULHI = 1 expresses them as the high half of a multiplication by 2^(32-n)
+// (IMAD.HI, FMA pipe) instead of SHF (ALU pipe): in k_chain<LAB,*> the ALU pipe is the busier one.  floor semantics = arithmetic
+// shift for negative values.  Experiment switch; see DESIGN.md for the measurement.
+#ifndef RV_LAB_MULHI
+#define RV_LAB_MULHI 0
+#endif
+template <int N>
+__device__ __forceinline__ int lab_shr(int x)
+{
+#if RV_LAB_MULHI
+    return __mulhi(x, 1 << (32 - N));
+#else
+    return x >> N;
+#endif
+}
+
 // A.2 forward, all three
 __device__ __forceinline__ void lab_fwd(const LabTabs *t, int B, int G, int R, int &L, int &a, int &bb)
 {
     const int r = t->g8[R], g = t->g8[G], b = t->g8[B];
-    const int fX = t->cb[(1777 * r + 1541 * g + 778 * b + 2048) >> 12];
-    const int fY = t->cb[(871 * r + 2929 * g + 296 * b + 2048) >> 12];
-    const int fZ = t->cb[(73 * r + 448 * g + 3575 * b + 2048) >> 12];
+    const int fX = t->cb[lab_shr<12>(1777 * r + 1541 * g + 778 * b + 2048)];
+    const int fY = t->cb[lab_shr<12>(871 * r + 2929 * g + 296 * b + 2048)];
+    const int fZ = t->cb[lab_shr<12>(73 * r + 448 * g + 3575 * b + 2048)];
     // over all 2^24 colours a stays in [42,226] and b in [20,223] (tests/test_oracle.py::test_lab_forward_ranges): no saturation needed
-    L = (296 * fY - 1336934 + 16384) >> 15;
-    a = (500 * (fX - fY) + ((128 << 15) + 16384)) >> 15;
-    bb = (200 * (fY - fZ) + ((128 << 15) + 16384)) >> 15;
+    L = lab_shr<15>(296 * fY - 1336934 + 16384);
+    a = lab_shr<15>(500 * (fX - fY) + ((128 << 15) + 16384));
+    bb = lab_shr<15>(200 * (fY - fZ) + ((128 << 15) + 16384));
 }
 __device__ __forceinline__ int lab_xz(int i)
 {
@@ -99,19 +115,19 @@ __device__ __forceinline__ void lab_inv_args(const LabTabs *t, int L, int a, int
 {
     y = t->yt[L];
     const int fy = t->ft[L];
-    const int adiv = ((5 * a * 53687 + 128) >> 13) - 4194;
-    const int bdiv = ((b * 41943 + 16) >> 9) - 10485 + 1;
+    const int adiv = lab_shr<13>(5 * a * 53687 + 128) - 4194;
+    const int bdiv = lab_shr<9>(b * 41943 + 16) - 10485 + 1;
     ix = fy + adiv;
     iz = fy - bdiv;
 }
 template <bool CUBIC_ONLY>
 __device__ __forceinline__ void lab_inv_tail(const LabTabs *t, int y, int ix, int iz, int &B, int &G, int &R)
 {
-    const int x = CUBIC_ONLY ? ((((ix * ix) >> 14) * ix) >> 14) : lab_xz(ix);
-    const int z = CUBIC_ONLY ? ((((iz * iz) >> 14) * iz) >> 14) : lab_xz(iz);
-    int ro = (12615 * x - 6296 * y - 2223 * z + 8192) >> 14;
-    int go = (-3773 * x + 7684 * y + 185 * z + 8192) >> 14;
-    int bo = (217 * x - 836 * y + 4715 * z + 8192) >> 14;
+    const int x = CUBIC_ONLY ? lab_shr<14>(lab_shr<14>(ix * ix) * ix) : lab_xz(ix);
+    const int z = CUBIC_ONLY ? lab_shr<14>(lab_shr<14>(iz * iz) * iz) : lab_xz(iz);
+    int ro = lab_shr<14>(12615 * x - 6296 * y - 2223 * z + 8192);
+    int go = lab_shr<14>(-3773 * x + 7684 * y + 185 * z + 8192);
+    int bo = lab_shr<14>(217 * x - 836 * y + 4715 * z + 8192);
     ro = min(max(ro, 0), 4095);
     go = min(max(go, 0), 4095);
     bo = min(max(bo, 0), 4095);

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include <cuda_fp16.h>
 
@@ -18,6 +19,23 @@ struct Geo {
     int tw, th;        // tile size of the (REFLECT_101-padded) plane, clahe.cpp semantics (A.3)
     float inv_tw, inv_th;
 };
+
+// Shared-memory index checks for the debug build (make librv_b200_dbg.so: -DRV_DEBUG_BOUNDS).  compute-sanitizer is closed on the
+// pool this code is developed on, so the hand-derived shared-memory bounds of k_chain / k_luma_hist / k_build_lut* are asserted
+// in-kernel instead: a violation prints the site and traps (the launch fails with an error, it never corrupts silently).  The
+// production build compiles the checks away.
+#ifdef RV_DEBUG_BOUNDS
+#define RV_CHECK_IDX(i, n, what)                                                                              \
+    do {                                                                                                      \
+        if ((long long)(i) < 0 || (long long)(i) >= (long long)(n)) {                                         \
+            printf("RV_DEBUG_BOUNDS: %s index %lld outside [0,%lld) at %s:%d block (%d,%d,%d) thread %d\n", what, (long long)(i), \
+                   (long long)(n), __FILE__, __LINE__, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);       \
+            __trap();                                                                                         \
+        }                                                                                                     \
+    } while (0)
+#else
+#define RV_CHECK_IDX(i, n, what) ((void)0)
+#endif
 
 __device__ __forceinline__ int sat8(int v) { return min(max(v, 0), 255); }
 

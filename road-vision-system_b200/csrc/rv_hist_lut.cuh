@@ -55,6 +55,7 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
         int v;
         if (SPACE == 1) v = lab_L_fast(tabs, B, G, R);
         else v = (4899 * R + 9617 * G + 1868 * B + 8192) >> 14;
+        RV_CHECK_IDX(v, 256, "histogram bin");
         atomicAdd(&myh[v], 1u);
         return v;
     };
@@ -287,6 +288,7 @@ k_build_lut_rows(const int32_t *__restrict__ hist, int grid, int clip, float lut
     const int ty = r ? min(qy, grid - 1) : max(qy - 1, 0);
     const size_t tile = (size_t)f * grid * grid + ty * grid + tx;
     const uint2 l8 = tile_lut_warp(hist + tile * 256, clip, lut_scale, lane);
+    RV_CHECK_IDX(w, 2 * grid, "sl (LUT rows)");
     *reinterpret_cast<uint2 *>(&sl[w][lane * 8]) = l8;
     if (lut != nullptr && r == 1 && qy < grid)                   // the lower tile row of quad row qy = tile row qy: written once
         *reinterpret_cast<uint2 *>(lut + tile * 256 + lane * 8) = l8;
@@ -295,6 +297,7 @@ k_build_lut_rows(const int32_t *__restrict__ hist, int grid, int clip, float lut
     for (int i = threadIdx.x; i < nq1 * 256; i += blockDim.x) {
         const int qx = i >> 8, v = i & 255;
         const int t1 = max(qx - 1, 0), t2 = min(qx, grid - 1);
+        RV_CHECK_IDX(grid + t2, 2 * LUT_ROWS_MAX_GRID, "sl (quad packing)");
         qo[i] = (uint32_t)sl[t1][v] | ((uint32_t)sl[t2][v] << 8) | ((uint32_t)sl[grid + t1][v] << 16) |
                 ((uint32_t)sl[grid + t2][v] << 24);
     }

@@ -35,10 +35,13 @@ def main():
     from oracle import cv2_chain
     import cv2
     cpu = "--no-cpu" not in sys.argv
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     ctx = rvb200.Context(0)
     st = torch.cuda.Stream(); torch.cuda.set_stream(st)
     pools = {}
     for name, (h, w), batch, space, grid, k in CONFIGS:
+        if only and only not in name:
+            continue
         if (h, w) not in pools:
             base = synth.frame_pool(1080, 1920, 4, base_seed=3000)
             if (h, w) == (1080, 1920):
@@ -79,6 +82,8 @@ def main():
     # C5: chain fused with letterbox + fp16 NCHW normalise to 640x640, batch 128 (1080p, YCrCb, k3 = default.yaml chain)
     from oracle import rv_oracle as O
     for k, want_full in ((3, False), (3, True), (5, False)):
+        if only:
+            break
         h, w, batch, size = 1080, 1920, 128, 640
         pool = pools[(h, w)]
         host = np.stack([pool[i % len(pool)] for i in range(batch)])
