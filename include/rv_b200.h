@@ -178,6 +178,38 @@ int rv_letterbox_f16(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t
 int rv_chain_letterbox_f16(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t in_pitch, const rv_params *p,
                            uint16_t *out, int S, int pad_value, uint8_t *full_out, size_t full_pitch, int mem_kind, void *stream);
 
+/* ---- fog synthesis: the per-pixel work of EnhancedFogSynthesizer.synthesize (src/augment/fog.py:227-299, driven by
+ * tools/fog_batch.py:7-34), the generator of the hot path's inputs.  The host side (road-vision-system_b200/augment/fog.py) draws
+ * every random number in the reference's order and builds the per-geometry maps; these two calls do the full-frame work on the GPU.
+ * rv_fog_set_geometry: depth prior and sky weight (h*w floats each, fog.py:144-170), the airlight ramps vgrad (h) and xgrad (w)
+ * (fog.py:133-134); host pointers, copied.  rv_fog_u8: one BGR frame in, one fogged BGR frame out (host pointers); `lattice` holds the
+ * octaves' (gh+1)*(gw+1) uniform lattices back to back (rand_perlin, fog.py:8-46); `noise` (optional, h*w*3 floats) is the sensor
+ * noise field when the host drew it, else the device generates one; t_out / beta_out / airlight_out (optional, host) receive the
+ * transmission map, the beta map (h*w floats each) and the scaled airlight map (h*w*3), the reference's `meta`. */
+typedef struct rv_fog_frame {
+    double persistence;     /* octave amplitude ratio of the value noise (0.5) */
+    float base_beta;        /* fog density drawn for this frame */
+    float A_bgr[3];         /* airlight colour after tint and clip (fog.py:120-131) */
+    float a_target;         /* mean the airlight map is scaled to (fog.py:258) */
+    float global_veil;
+    float glow;             /* glow strength */
+    float cdrop;            /* local contrast fade amount */
+    float tint[3];
+    float gamma;            /* 0 = no gamma step */
+    float noise_sigma;      /* 0 = no sensor noise */
+    uint32_t noise_seed;    /* device generator, used when `noise` is NULL */
+    int32_t octaves;        /* 1..4 */
+    int32_t lat_gh[4], lat_gw[4];
+    int32_t band_rad[3];    /* Gaussian sizes of the three depth-blur bands, <= 1 = band skipped (fog.py:207-216) */
+    int32_t glow_k, glow_k2;/* Gaussian sizes of the glow mask and the glow blur (fog.py:193, 196) */
+    int32_t fade_d;         /* bilateral diameter of the contrast fade (fog.py:227) */
+    float fade_sigma;       /* its sigma, 25 + 50 * cdrop */
+    int32_t edge_guided;
+} rv_fog_frame;
+int rv_fog_set_geometry(rv_ctx *ctx, int h, int w, const float *depth, const float *sky_weight, const float *vgrad, const float *xgrad);
+int rv_fog_u8(rv_ctx *ctx, const uint8_t *in, uint8_t *out, int h, int w, const rv_fog_frame *f, const float *lattice, const float *noise,
+              float *t_out, float *beta_out, float *airlight_out);
+
 /* span: n ints = max(gray) - min(gray) per frame */
 int rv_gray_span(rv_ctx *ctx, const uint8_t *in, int n, int h, int w, size_t pitch, int32_t *span, int mem_kind);
 

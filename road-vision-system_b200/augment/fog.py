@@ -1,0 +1,232 @@
+"""EnhancedFogSynthesizer on the GPU -- same class name, constructor and `synthesize(bgr) -> (hazy, meta)` contract as
+/root/reference/src/augment/fog.py:84-299 (driven by tools/fog_batch.py:7-34), which costs 1-2 s per 1080p frame on the CPU.
+
+Division of labour (details in csrc/rv_fog.cu):
+
+* host, per synthesizer: the random stream.  Every draw is made here with numpy's RandomState, in the order the reference makes
+  them (density, lattice seed, airlight tint, airlight target, glow, contrast drop, colour tint, gamma decision, noise decision),
+  so a given seed selects the same fog parameters as in the reference;
+* host, per geometry (cached): the depth prior and the sky weight (closed forms over the pixel grid) and the two airlight ramps;
+* host, per frame: the airlight colour from the brightest tenth of the top band (a quantile over 12 % of the frame);
+* device, per frame: everything else -- value noise, transmission, both edge-preserving filters, composition, veil, glow,
+  depth blur, contrast fade, tint / gamma / sensor noise (rv_fog_u8).
+
+There is no CPU fallback: without the CUDA library and a B200 `synthesize` raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .._native import default_context
+
+FOG_PRESETS = {
+    # level: fog density, airlight mean, glow strength, contrast drop -- the ranges of fog.py:72-76
+    "light": {"beta": (0.03, 0.06), "airlight": (0.82, 0.93), "glow": (0.12, 0.22), "contrast_drop": (0.06, 0.12)},
+    "medium": {"beta": (0.06, 0.12), "airlight": (0.86, 0.96), "glow": (0.18, 0.34), "contrast_drop": (0.10, 0.18)},
+    "heavy": {"beta": (0.12, 0.22), "airlight": (0.90, 0.99), "glow": (0.28, 0.48), "contrast_drop": (0.15, 0.26)},
+}
+_MOR_RANGES = {"airlight": (0.86, 0.98), "glow": (0.12, 0.45), "contrast_drop": (0.08, 0.22)}      # fog.py:244-247
+
+
+class FogFrame(C.Structure):
+    """rv_fog_frame (include/rv_b200.h)"""
+    _fields_ = [
+        ("persistence", C.c_double), ("base_beta", C.c_float), ("A_bgr", C.c_float * 3), ("a_target", C.c_float),
+        ("global_veil", C.c_float), ("glow", C.c_float), ("cdrop", C.c_float), ("tint", C.c_float * 3), ("gamma", C.c_float),
+        ("noise_sigma", C.c_float), ("noise_seed", C.c_uint32), ("octaves", C.c_int32), ("lat_gh", C.c_int32 * 4),
+        ("lat_gw", C.c_int32 * 4), ("band_rad", C.c_int32 * 3), ("glow_k", C.c_int32), ("glow_k2", C.c_int32), ("fade_d", C.c_int32),
+        ("fade_sigma", C.c_float), ("edge_guided", C.c_int32),
+    ]
+
+
+def _logistic(z):
+    return 1.0 / (1.0 + np.exp(-z))
+
+
+class EnhancedFogSynthesizer:
+    def __init__(self, level="medium", mor=None, y_h_ratio=0.42, vanishing_x_ratio=0.5, perlin_scale_ratio=0.18, perlin_octaves=2,
+                 sky_boost=1.25, road_damp=0.9, edge_guided=True, horizon_softness=0.06, depth_blur_max=3.5, global_veil=0.06,
+                 seed=None, context=None, exact_noise=False):
+        """Reference arguments (fog.py:92-105) plus two of this package's own: `context` (rvb200.Context; default: the process-wide
+        one) and `exact_noise` (draw the sensor-noise field on the host from the same random stream as the reference, 6 M normals per
+        1080p frame, instead of generating it on the device)."""
+        self.level, self.mor = level, mor
+        self.y_h_ratio, self.vx_ratio = y_h_ratio, vanishing_x_ratio
+        self.perlin_scale_ratio, self.perlin_octaves = perlin_scale_ratio, perlin_octaves
+        self.sky_boost, self.road_damp = sky_boost, road_damp
+        self.edge_guided = edge_guided
+        self.horizon_softness, self.depth_blur_max, self.global_veil = horizon_softness, depth_blur_max, global_veil
+        self.rng = np.random.RandomState(seed) if seed is not None else np.random
+        self.exact_noise = exact_noise
+        self._context = context
+        self._geo = None            # (h, w, key) of the maps currently uploaded to the context
+
+    # ---- per-geometry maps (fog.py:144-170 and the ramps of :133-134) ------------------------------------------------------
+    def _geometry(self, h, w):
+        horizon = int(self.y_h_ratio * h)
+        rows = np.arange(h, dtype=np.float32)[:, None] + np.zeros((1, w), np.float32)
+        cols = np.arange(w, dtype=np.float32)[None, :] + np.zeros((h, 1), np.float32)
+        below = np.maximum(rows - horizon, 1.0)                       # perspective term: 1 / distance below the horizon line
+        persp = 1.0 / below
+        vx, vy = float(self.vx_ratio * w), float(horizon)
+        radial = 1.0 / (np.sqrt((cols - vx) ** 2 + (rows - vy) ** 2) + 1.0)     # farther towards the vanishing point
+        depth = 0.7 * (persp / persp.max()) + 0.3 * (radial / radial.max())
+        depth = (depth - depth.min()) / max(1e-6, (depth.max() - depth.min()))
+        soft = max(1e-3, self.horizon_softness) * h
+        sky = _logistic((horizon - rows) / soft).astype(np.float32)  # ~1 above the horizon, ~0 below, S-shaped across it
+        depth = depth * ((1.0 + (self.sky_boost - 1.0) * sky) * (self.road_damp ** (1.0 - sky)))
+        depth = np.clip(depth, 0, 1).astype(np.float32)
+        vgrad = np.linspace(1.0, 0.85, h, dtype=np.float32)
+        xgrad = np.linspace(0.95, 1.05, w, dtype=np.float32)
+        # mean depth of the three blur bands (fog.py:206-212): the band radius is depth_blur_max (0.5 + beta) mean(depth in band)
+        bands, lo = [], 0.0
+        for hi in (0.33, 0.66, 1.0):
+            sel = (depth >= np.float32(lo)) & (depth < np.float32(hi))
+            bands.append((int(sel.sum()), depth[sel] if sel.any() else None))
+            lo = hi
+        return {"h": h, "w": w, "horizon": horizon, "depth": depth, "sky": sky, "vgrad": vgrad, "xgrad": xgrad, "bands": bands}
+
+    def _ctx(self):
+        return self._context if self._context is not None else default_context()
+
+    def _ensure_geometry(self, h, w):
+        key = (h, w, self.y_h_ratio, self.vx_ratio, self.sky_boost, self.road_damp, self.horizon_softness)
+        ctx = self._ctx()
+        if self._geo is None or self._geo["key"] != key:
+            self._geo = self._geometry(h, w)
+            self._geo["key"] = key
+            self._geo["uploaded_to"] = None
+        # one geometry lives on a context at a time; several synthesizers may share the context
+        if self._geo["uploaded_to"] is not ctx or getattr(ctx, "_fog_geo_key", None) != (id(self), key):
+            g = self._geo
+            fp = C.POINTER(C.c_float)
+            ctx._ck(ctx._lib.rv_fog_set_geometry(ctx._h, h, w, g["depth"].ctypes.data_as(fp), g["sky"].ctypes.data_as(fp),
+                                                 g["vgrad"].ctypes.data_as(fp), g["xgrad"].ctypes.data_as(fp)))
+            g["uploaded_to"] = ctx
+            ctx._fog_geo_key = (id(self), key)
+        return self._geo
+
+    # ---- per-frame host work --------------------------------------------------------------------------------------------------
+    def _uniform(self, lo, hi):
+        return float(lo + (hi - lo) * self.rng.rand())
+
+    def _lattices(self, h, w):
+        """The uniform lattices of the value noise, drawn exactly like rand_perlin draws them (fog.py:13-23), and their sizes."""
+        scale = max(16, int(self.perlin_scale_ratio * w))
+        lattice_rng = np.random.RandomState(self.rng.randint(1e9))
+        freq, shapes, chunks = 1.0 / max(1, scale), [], []
+        for _ in range(max(1, self.perlin_octaves)):
+            gh, gw = max(1, int(h * freq)), max(1, int(w * freq))
+            chunks.append(lattice_rng.rand(gh + 1, gw + 1).astype(np.float32).ravel())
+            shapes.append((gh, gw))
+            freq *= 2.0
+        return shapes, np.concatenate(chunks)
+
+    def _airlight_colour(self, bgr):
+        """Mean colour of the brightest tenth of the top 12 % of the frame, tinted and clipped (fog.py:120-131)."""
+        h = bgr.shape[0]
+        top = bgr[:max(10, int(0.12 * h))].astype(np.float32) / 255.0
+        lum = 0.299 * top[:, :, 2] + 0.587 * top[:, :, 1] + 0.114 * top[:, :, 0]
+        bright = lum >= np.quantile(lum, 0.9)
+        colour = (top[bright].mean(axis=0) if bright.sum() >= 100 else top.mean(axis=(0, 1))).astype(np.float32)
+        tint = self.rng.uniform(-0.02, 0.02, size=3).astype(np.float32)
+        return np.clip(colour + tint, 0.7, 1.0)
+
+    def synthesize(self, bgr_uint8, level=None):
+        """BGR uint8 frame -> (hazy BGR uint8 frame, meta with beta_map / A_map / depth / y_h / t), as fog.py:227-299."""
+        if not isinstance(bgr_uint8, np.ndarray) or bgr_uint8.dtype != np.uint8 or bgr_uint8.ndim != 3 or bgr_uint8.shape[2] != 3:
+            raise ValueError("synthesize expects a (H,W,3) uint8 BGR frame")
+        frame = np.ascontiguousarray(bgr_uint8)
+        h, w = frame.shape[:2]
+        if level is not None:
+            self.level = level
+        ctx = self._ctx()
+        octaves = max(1, int(self.perlin_octaves))
+        if octaves > 4:
+            raise ValueError("at most 4 noise octaves are supported")
+
+        # the reference's draws, in its order
+        if self.mor is not None and self.mor > 0:
+            base_beta, ranges = 3.912 / float(self.mor), _MOR_RANGES             # Koschmieder, fog.py:243
+        else:
+            ranges = FOG_PRESETS[self.level]
+            base_beta = self._uniform(*ranges["beta"])
+        geo = self._ensure_geometry(h, w)
+        shapes, lattice = self._lattices(h, w)
+        colour = self._airlight_colour(frame)
+        a_target = self._uniform(*ranges["airlight"])
+        glow = self._uniform(*ranges["glow"])
+        cdrop = self._uniform(*ranges["contrast_drop"])
+        tint = (1.0 + self.rng.uniform(-0.015, 0.02, size=3)).astype(np.float32)
+        gamma = (1.0 + self.rng.uniform(-0.04, 0.05)) if self.rng.rand() < 0.35 else 0.0
+        noisy = self.rng.rand() < 0.3
+        noise = None
+        if noisy and self.exact_noise:
+            noise = np.ascontiguousarray(self.rng.normal(0, 0.0035, size=frame.shape).astype(np.float32))
+
+        f = FogFrame()
+        f.persistence, f.base_beta = 0.5, base_beta
+        f.A_bgr[:] = [float(v) for v in colour]
+        f.a_target, f.global_veil, f.glow, f.cdrop = a_target, float(self.global_veil), glow, cdrop
+        f.tint[:] = [float(v) for v in tint]
+        f.gamma = float(gamma)
+        f.noise_sigma = 0.0035 if noisy else 0.0
+        f.noise_seed = int(self.rng.randint(1 << 31)) if (noisy and noise is None) else 0
+        f.octaves = octaves
+        for i, (gh, gw) in enumerate(shapes):
+            f.lat_gh[i], f.lat_gw[i] = gh, gw
+        # depth-blur band sizes: int(max(1, 1.5 * mean(r in band))) | 1 with r = depth * depth_blur_max * (0.5 + beta), fog.py:203-213
+        for i, (count, vals) in enumerate(geo["bands"]):
+            rad = 0
+            if count >= 100:
+                r = np.clip(vals * self.depth_blur_max * (0.5 + base_beta), 0.0, self.depth_blur_max * 1.5)
+                rad = int(max(1, np.mean(r) * 1.5)) | 1
+            f.band_rad[i] = rad if rad > 1 else 0
+        f.glow_k = int(9 + 20 * glow) | 1
+        f.glow_k2 = int(max(7, (h + w) * (0.003 + 0.01 * glow))) | 1
+        f.fade_d = int(5 + cdrop * 20) | 1
+        f.fade_sigma = 25 + cdrop * 50
+        f.edge_guided = 1 if self.edge_guided else 0
+
+        out = np.empty_like(frame)
+        t = np.empty((h, w), np.float32)
+        beta = np.empty((h, w), np.float32)
+        amap = np.empty((h, w, 3), np.float32)
+        fp = C.POINTER(C.c_float)
+        ctx._ck(ctx._lib.rv_fog_u8(ctx._h, frame.ctypes.data, out.ctypes.data, h, w, C.byref(f), lattice.ctypes.data_as(fp),
+                                   noise.ctypes.data_as(fp) if noise is not None else None, t.ctypes.data_as(fp),
+                                   beta.ctypes.data_as(fp), amap.ctypes.data_as(fp)))
+        return out, {"beta_map": beta, "A_map": amap, "depth": geo["depth"], "y_h": geo["horizon"], "t": t}
+
+
+def process_folder(inp, outp, levels=("light", "medium", "heavy"), limit=None, seed=None, context=None):
+    """tools/fog_batch.py:7-34 on the GPU: every .jpg / .png / .jpeg below `inp` (recursively) at every level with fog_batch's
+    parameters (:19-27), written to `outp/<level>/<relative path>`.  `seed` (new) makes the run reproducible.  Image decoding and
+    encoding use cv2 (I/O only).  Returns the number of files written."""
+    import cv2
+    files = []
+    for dirpath, _, names in os.walk(inp):
+        files += [os.path.join(dirpath, n) for n in names if os.path.splitext(n)[1].lower() in (".jpg", ".png", ".jpeg")]
+    files.sort()
+    if limit:
+        files = files[:limit]
+    written = 0
+    for i, path in enumerate(files, 1):
+        img = cv2.imread(path)
+        if img is None:
+            print("Skip unreadable:", path)
+            continue
+        rel = os.path.relpath(path, inp)
+        for j, level in enumerate(levels):
+            synth = EnhancedFogSynthesizer(level=level, y_h_ratio=0.42, perlin_scale_ratio=0.18, perlin_octaves=2, horizon_softness=0.07,
+                                           global_veil=0.5, depth_blur_max=4.0, context=context,
+                                           seed=None if seed is None else seed + 3 * (i - 1) + j)
+            hazy, _ = synth.synthesize(img)
+            dest = os.path.join(outp, level, rel)
+            os.makedirs(os.path.dirname(dest), exist_ok=True)
+            cv2.imwrite(dest, hazy)
+            written += 1
+        if i % 20 == 0:
+            print(f"[{i}/{len(files)}] {path}")
+    return written

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "rv_kernels.cuh"
+#include "rv_internal.h"
 
 using namespace rv;
 
@@ -92,6 +93,8 @@ struct rv_ctx {
     cudaStream_t fstream = nullptr;         // single-frame path (per-frame plugin contract): its own stream, workspace set and graphs
     std::vector<struct FrameGraph> fgraphs;
     int32_t *fflag = nullptr;               // page-locked: gate decision of the single-frame path
+    void *fog = nullptr;                    // state of rv_fog.cu (fog synthesis), destroyed through fog_destroy
+    void (*fog_destroy)(void *) = nullptr;
     long frame_graphs = 1;                  // option "frame_graphs": 0 = the single-frame path launches directly (no CUDA graph)
     std::vector<ColTab> coltabs;
     std::vector<LbTab> lbtabs;
@@ -966,6 +969,22 @@ int check_lb_args(rv_ctx *ctx, const void *tensor, int S, int pad_value)
 
 }  // namespace
 
+int rv_internal_device(const rv_ctx *ctx) { return ctx->device; }
+void *rv_internal_stream(rv_ctx *ctx) { return ctx->stream; }
+int rv_internal_fail(rv_ctx *ctx, int code, const char *fmt, ...)
+{
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+void rv_internal_count_launches(rv_ctx *ctx, long n) { ctx->launches += n; }
+void *rv_internal_get_fog(rv_ctx *ctx) { return ctx->fog; }
+void rv_internal_set_fog(rv_ctx *ctx, void *state, void (*destroy)(void *)) { ctx->fog = state; ctx->fog_destroy = destroy; }
+
 extern "C" {
 
 const char *rv_version(void) { return "rv_b200 0.1 (sm_100a)"; }
@@ -1059,6 +1078,7 @@ void rv_destroy(rv_ctx *ctx)
     for (WsSync &w : ctx->wsync)
         if (w.ev) cudaEventDestroy(w.ev);
     drop_frame_graphs(ctx);
+    if (ctx->fog && ctx->fog_destroy) ctx->fog_destroy(ctx->fog);
     if (ctx->fstream) cudaStreamDestroy(ctx->fstream);
     if (ctx->fflag) cudaFreeHost(ctx->fflag);
     for (const TimedLaunch &t : ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
