@@ -56,7 +56,12 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")) and f != "rv_lab_tables.h":
                 text = open(os.path.join(dirpath, f)).read()
                 assert "rv_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
-                assert "import cv2" not in text or f == "capture.py", f
+                # cv2 may only appear for I/O: the camera in capture.py, image files in augment/fog.py's folder tool
+                if f == "fog.py":
+                    import re as _re
+                    assert set(_re.findall(r"cv2\.(\w+)", text)) <= {"imread", "imwrite"}, f
+                else:
+                    assert "import cv2" not in text or f == "capture.py", f
 
 
 def test_pipeline_identity_and_construction():
