@@ -133,8 +133,9 @@ class EnhancedFogSynthesizer:
         tint = self.rng.uniform(-0.02, 0.02, size=3).astype(np.float32)
         return np.clip(colour + tint, 0.7, 1.0)
 
-    def synthesize(self, bgr_uint8, level=None):
-        """BGR uint8 frame -> (hazy BGR uint8 frame, meta with beta_map / A_map / depth / y_h / t), as fog.py:227-299."""
+    def synthesize(self, bgr_uint8, level=None, meta=True):
+        """BGR uint8 frame -> (hazy BGR uint8 frame, meta with beta_map / A_map / depth / y_h / t), as fog.py:227-299.
+        `meta=False` (new) skips the download of the three float maps (41 MB at 1080p) and returns only depth and y_h."""
         if not isinstance(bgr_uint8, np.ndarray) or bgr_uint8.dtype != np.uint8 or bgr_uint8.ndim != 3 or bgr_uint8.shape[2] != 3:
             raise ValueError("synthesize expects a (H,W,3) uint8 BGR frame")
         frame = np.ascontiguousarray(bgr_uint8)
@@ -190,14 +191,15 @@ class EnhancedFogSynthesizer:
         f.edge_guided = 1 if self.edge_guided else 0
 
         out = np.empty_like(frame)
-        t = np.empty((h, w), np.float32)
-        beta = np.empty((h, w), np.float32)
-        amap = np.empty((h, w, 3), np.float32)
         fp = C.POINTER(C.c_float)
+        info = {"depth": geo["depth"], "y_h": geo["horizon"]}
+        if meta:
+            info.update({"t": np.empty((h, w), np.float32), "beta_map": np.empty((h, w), np.float32), "A_map": np.empty((h, w, 3), np.float32)})
         ctx._ck(ctx._lib.rv_fog_u8(ctx._h, frame.ctypes.data, out.ctypes.data, h, w, C.byref(f), lattice.ctypes.data_as(fp),
-                                   noise.ctypes.data_as(fp) if noise is not None else None, t.ctypes.data_as(fp),
-                                   beta.ctypes.data_as(fp), amap.ctypes.data_as(fp)))
-        return out, {"beta_map": beta, "A_map": amap, "depth": geo["depth"], "y_h": geo["horizon"], "t": t}
+                                   noise.ctypes.data_as(fp) if noise is not None else None,
+                                   info["t"].ctypes.data_as(fp) if meta else None, info["beta_map"].ctypes.data_as(fp) if meta else None,
+                                   info["A_map"].ctypes.data_as(fp) if meta else None))
+        return out, info
 
 
 def process_folder(inp, outp, levels=("light", "medium", "heavy"), limit=None, seed=None, context=None):
@@ -222,7 +224,7 @@ def process_folder(inp, outp, levels=("light", "medium", "heavy"), limit=None, s
             synth = EnhancedFogSynthesizer(level=level, y_h_ratio=0.42, perlin_scale_ratio=0.18, perlin_octaves=2, horizon_softness=0.07,
                                            global_veil=0.5, depth_blur_max=4.0, context=context,
                                            seed=None if seed is None else seed + 3 * (i - 1) + j)
-            hazy, _ = synth.synthesize(img)
+            hazy, _ = synth.synthesize(img, meta=False)
             dest = os.path.join(outp, level, rel)
             os.makedirs(os.path.dirname(dest), exist_ok=True)
             cv2.imwrite(dest, hazy)

@@ -191,3 +191,17 @@ def test_ycc_chroma_table_equals_oracle_round_trip_exhaustive():
         want = O.ycrcb2bgr(np.stack([y2.astype(np.uint8), ycc[..., 1], ycc[..., 2]], -1))
         got = np.stack([np.clip(y2 + fB, 0, 255), np.clip(y2 + g - 256, 0, 255), np.clip(y2 + fR, 0, 255)], -1).astype(np.uint8)
         assert np.array_equal(got, want), shift
+
+
+def test_profile_constants_belong_to_the_shipped_kernels():
+    """bench.py reports DRAM traffic and instruction counts from profiles/final_k_chain.json; the capture must have been taken on
+    exactly the kernel sources in the tree (hash over csrc/Makefile + the kernel headers), else the numbers are stale."""
+    import json
+    import rvb200
+    tree = rvb200.kernel_source_hash()
+    for name in ("final_k_chain.json", "final_k_luma_hist.json", "final_k_chain_lab_k3.json", "final_k_chain_lab_k5.json"):
+        j = json.load(open(os.path.join(ROOT, "profiles", name)))
+        assert j["source_hash"] == tree, f"profiles/{name} was captured on {j['source_hash']}, the tree is {tree}: re-capture (tools/gpu_r2e.sh)"
+        assert j["dram_bytes_read"] > 0 and j["warp_instructions"] > 0
+    j = json.load(open(os.path.join(ROOT, "profiles", "final_k_chain.json")))
+    assert "k_chain<0, 5>" in j["kernel"] and j["grid"] == "(16, 23, 64)"
