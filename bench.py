@@ -311,7 +311,7 @@ def stream_leg(rvb200, local_rank, pool, seconds, fps, skip_s=2.0):
     ctx = rvb200.Context(local_rank)
     pipe = rvb200.PreprocessPipeline(CHAIN_CFG, context=ctx)
     nframes = int(seconds * fps)
-    vs = rvb200.VideoSource(reader=SyntheticReader(list(pool[:4]), limit=nframes))
+    vs = rvb200.VideoSource(reader=SyntheticReader(list(pool[:4]), limit=nframes), pinned=None)   # the feeder's ring is the pinned memory
     feeder = rvb200.BatchFeeder(vs, batch=1, shape=(H, W, 3), alloc=ctx.pinned_empty, depth=3, fps=fps)
     out = ctx.pinned_empty((1, H, W, 3))
     warm = ctx.pinned_empty((1, H, W, 3))

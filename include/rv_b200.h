@@ -93,7 +93,10 @@ const char *rv_last_error(const rv_ctx *ctx);
  * the next group runs on a high-priority side stream under the current group's k_chain; measured 1-6 % slower on
  * B200 because k_chain leaves no SM resources for co-resident CTAs);
  * "frame_graphs" (default 1: single-frame host calls -- rv_chain_u8 with n = 1 and contiguous rows, i.e. the per-frame plugin
- * contract -- replay one captured CUDA graph per (shape, parameters) between the two copies; 0 = direct launches). */
+ * contract -- replay one captured CUDA graph per (shape, parameters) between the two copies; 0 = direct launches);
+ * "stage_threads" (default 0 = pageable single-frame input is left to the driver's own staged copy; n > 0: n helper threads and the
+ * caller stage a pageable frame of >= 1.5 MB into page-locked memory slice by slice while earlier slices are already being uploaded
+ * -- measured 2x SLOWER than the driver on B200 hosts, kept as an option). */
 int rv_set_option(rv_ctx *ctx, const char *name, long value);
 /* kernels launched by this context since creation (for bench accounting) */
 long rv_launch_count(const rv_ctx *ctx);

@@ -46,6 +46,12 @@ for (h, w, space, k) in [(480, 640, "YCrCb", 3), (720, 1280, "YCrCb", 3), (720, 
             assert out is not src and out.flags.writeable
             row[f"{name}_{'graph' if graphs else 'direct'}_ms_p50"], row[f"{name}_{'graph' if graphs else 'direct'}_ms_min"] = p50(lambda: pipe(src))
     ctx.set_option("frame_graphs", 1)
+    ctx.set_option("stage_threads", 3)                       # experiment: helper threads stage pageable input (default: the driver does)
+    for _ in range(3):
+        out = pipe(img)
+    assert np.array_equal(out, want)
+    row["pageable_graph_helper_threads_ms_p50"], _ = p50(lambda: pipe(img))
+    ctx.set_option("stage_threads", 0)
     # floor: the two PCIe copies of one frame, back to back, nothing else
     dev = rvb200.DeviceArray(ctx, img.shape)
     res = ctx.pinned_empty(img.shape)

@@ -552,3 +552,48 @@ def test_batch_feeder_pinned_ring_to_process_batch(ctx):
     assert seen == nframes and counts == [8, 8, 7]
     assert all(t > 0 for t in ts_all) and np.all(np.diff(ts_all) >= 0)
     pctx.close()
+
+
+def test_single_frame_path_staging_and_graphs(ctx):
+    """The per-frame contract's fast path: pageable frames (staged by the driver, or by the optional helper threads), page-locked frames uploaded
+    directly, CUDA-graph replay vs direct launches, shapes and parameters alternating between calls (graph cache, staging-frame
+    growth, workspace reallocation) -- every variant gives the oracle's bytes, call after call."""
+    import rvb200
+    from rvb200 import synth
+    shapes = [(720, 1280), (1080, 1920), (480, 640), (1080, 1920), (2160, 3840), (720, 1280)]
+    frames = {s: synth.road_frame(s[0], s[1], 600 + i) for i, s in enumerate(dict.fromkeys(shapes))}
+    params = [("YCrCb", 8, 5), ("LAB", 8, 3), ("YCrCb", 16, 3)]
+    want = {}
+    for s, f in frames.items():
+        for (space, grid, k) in params:
+            if s == (2160, 3840) and space == "LAB":
+                continue
+            want[(s, space, grid, k)] = O.chain(f, ospace(space), 2.0, grid, k)
+    pinned = {}
+    for s, f in frames.items():
+        pinned[s] = ctx.pinned_empty(f.shape)
+        pinned[s][:] = f
+    try:
+        for rnd in range(3):
+            ctx.set_option("frame_graphs", 0 if rnd == 1 else 1)
+            ctx.set_option("stage_threads", 3 if rnd == 2 else 0)
+            for s in shapes:
+                for (space, grid, k) in params:
+                    if (s, space, grid, k) not in want:
+                        continue
+                    p = rvb200.Params.make(space, 2.0, grid, k)
+                    for src in (frames[s], pinned[s], frames[s]):
+                        got = ctx.chain(src[None], p)[0]
+                        assert np.array_equal(got, want[(s, space, grid, k)]), (rnd, s, space, grid, k)
+        # back-to-back pageable frames of one shape with different contents: the staging frame is reused every call
+        ctx.set_option("frame_graphs", 1)
+        ctx.set_option("stage_threads", 3)                      # (the optional helper-thread staging; default is off)
+        p = rvb200.Params.make("YCrCb", 2.0, 8, 5)
+        a, b = frames[(1080, 1920)], synth.road_frame(1080, 1920, 777)
+        wa, wb = want[((1080, 1920), "YCrCb", 8, 5)], O.chain(b, O.SPACE_YCRCB, 2.0, 8, 5)
+        for i in range(40):
+            src, w_ = (a, wa) if i % 2 == 0 else (b, wb)
+            assert np.array_equal(ctx.chain(src[None], p)[0], w_), i
+    finally:
+        ctx.set_option("frame_graphs", 1)
+        ctx.set_option("stage_threads", 0)

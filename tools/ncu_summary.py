@@ -45,7 +45,7 @@ def write_json(path, rep, hdr, d):
     def to_us(name):
         u = unit[name].lower()
         return num(name) * {'ns': 1e-3, 'us': 1, 'usecond': 1, 'nsecond': 1e-3, 'ms': 1e3, 'msecond': 1e3}[u]
-    j = {"kernel": d[hdr.index('Kernel Name')], "capture": os.path.basename(rep), "source_hash": rvb200.kernel_source_hash(),
+    j = {"kernel": d[hdr.index('Kernel Name')], "capture": os.path.basename(rep), "source_hash": HASH[0] if HASH else rvb200.kernel_source_hash(),
          "grid": d[hdr.index('Grid Size')] if 'Grid Size' in hdr else None,
          "dram_bytes_read": to_bytes('dram__bytes_read.sum'), "dram_bytes_write": to_bytes('dram__bytes_write.sum'),
          "warp_instructions": num('smsp__inst_executed.sum'), "duration_us_under_ncu": to_us('gpu__time_duration.sum'),
@@ -61,11 +61,16 @@ def write_json(path, rep, hdr, d):
 
 
 UNITS = []
+HASH = []
 
 
 def main():
     args = list(sys.argv[1:])
     jpath = None
+    if '--hash-file' in args:                       # hash recorded on the GPU box when the capture was taken
+        i = args.index('--hash-file')
+        HASH[:] = [open(args[i + 1]).read().strip()]
+        del args[i:i + 2]
     if '--json' in args:
         i = args.index('--json')
         jpath = args[i + 1]
