@@ -597,3 +597,41 @@ def test_single_frame_path_staging_and_graphs(ctx):
     finally:
         ctx.set_option("frame_graphs", 1)
         ctx.set_option("stage_threads", 0)
+
+
+def test_contexts_are_independent_across_threads():
+    """A context is for one thread at a time; DIFFERENT contexts may run concurrently from different threads (one per camera stream).
+    Three threads, each with its own Context and pipeline, mix per-frame calls (graph capture and replay), batch calls and the gate."""
+    import threading
+    import rvb200
+    from rvb200 import synth
+    jobs = [("YCrCb", 8, 5, (360, 640)), ("LAB", 8, 3, (270, 480)), ("YCrCb", 4, 3, (480, 640))]
+    data = []
+    for i, (space, grid, k, (h, w)) in enumerate(jobs):
+        fr = synth.frame_pool(h, w, 4, base_seed=800 + 10 * i)
+        data.append((fr, [O.chain(f, ospace(space), 2.0, grid, k) for f in fr]))
+    errors = []
+
+    def work(i):
+        try:
+            space, grid, k, _ = jobs[i]
+            fr, want = data[i]
+            c = rvb200.Context(0)
+            pl = rvb200.PreprocessPipeline({"chain": [{"name": "CLAHEDehaze", "params": {"space": space, "tile_grid": grid}},
+                                                      {"name": "MedianDerain", "params": {"ksize": k}}]}, context=c)
+            for rep in range(25):
+                j = rep % len(fr)
+                if not np.array_equal(pl(fr[j]), want[j]):
+                    raise AssertionError(f"thread {i} frame call {rep}")
+                if rep % 5 == 0 and not np.array_equal(pl.process_batch(fr), np.stack(want)):
+                    raise AssertionError(f"thread {i} batch call {rep}")
+            c.close()
+        except Exception as e:          # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
