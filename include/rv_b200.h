@@ -152,8 +152,11 @@ typedef struct rv_io {
     int32_t in_kind, out_kind, tensor_kind;
     int32_t tensor_size;    /* S of the S x S letterbox */
     int32_t pad_value;      /* 114 in ultralytics */
-    int32_t reserved;
+    int32_t tensor_flags;   /* RV_TENSOR_PADDING_PRESENT: a HOST tensor buffer already holds the padding rows (written once, e.g. with
+                             * pad_value / 255 as a half): only the image rows [top, top + new_h) of every plane are copied back, which
+                             * is 56 % of a 1080p -> 640 x 640 tensor; rv_letterbox_geometry gives top and new_h */
 } rv_io;
+enum { RV_TENSOR_PADDING_PRESENT = 1 };
 int rv_submit_io(rv_ctx *ctx, const rv_io *io, int n, int h, int w, const rv_params *p);
 
 /* Stage-level entry points (parity tests). All synchronous; mem_kind applies to every pointer. */

@@ -39,7 +39,7 @@ class IO(C.Structure):
         ("in_", C.c_void_p), ("in_pitch", C.c_size_t), ("out", C.c_void_p), ("out_pitch", C.c_size_t),
         ("tensor", C.c_void_p), ("processed", C.c_void_p),
         ("in_kind", C.c_int32), ("out_kind", C.c_int32), ("tensor_kind", C.c_int32),
-        ("tensor_size", C.c_int32), ("pad_value", C.c_int32), ("reserved", C.c_int32),
+        ("tensor_size", C.c_int32), ("pad_value", C.c_int32), ("tensor_flags", C.c_int32),
     ]
 
 
@@ -376,7 +376,17 @@ class Context:
             return int(x.__cuda_array_interface__["data"][0]), MEM_DEVICE
         return int(x), MEM_DEVICE
 
-    def submit_io(self, frames, params, shape=None, out=None, tensor=None, size=640, pad_value=114, processed=None):
+    def fill_tensor_padding(self, tensor, h, w, size=640, pad_value=114):
+        """Write the letterbox padding (pad_value / 255 as a half) into the rows above and below the image of a host
+        (B,3,size,size) float16 array for (h, w) frames.  A buffer prepared like this once (a ring of pinned tensors) can be
+        handed to process_batch_to_tensor(..., padding_present=True): only the image rows then cross PCIe on the way back."""
+        nw, nh, top, left, _ = self.letterbox_geometry(h, w, size)
+        v = np.float16(np.float32(pad_value) / np.float32(255))
+        tensor[:, :, :top, :] = v
+        tensor[:, :, top + nh:, :] = v
+        return tensor
+
+    def submit_io(self, frames, params, shape=None, out=None, tensor=None, size=640, pad_value=114, processed=None, padding_present=False):
         """rv_submit_io: asynchronous job whose ends live independently on the host or on the GPU; call wait() afterwards.
 
         frames: (N,H,W,3) uint8 numpy array (pinned or pageable) or a device object / pointer (then pass shape=(N,H,W)).
@@ -394,6 +404,7 @@ class Context:
         io.out_pitch = 3 * w
         io.tensor, io.tensor_kind = self._end(tensor)
         io.tensor_size, io.pad_value = int(size), int(pad_value)
+        io.tensor_flags = 1 if padding_present else 0
         io.processed = processed.ctypes.data if processed is not None else None
         self._ck(self._lib.rv_submit_io(self._h, C.byref(io), n, h, w, C.byref(params)))
 
@@ -454,8 +465,19 @@ class Context:
         self._ck(self._lib.rv_letterbox_f16(self._h, frames.ctypes.data, n, h, w, 3 * w, out.ctypes.data, size, pad_value, MEM_HOST))
         return out
 
-    def chain_letterbox(self, frames, params, size=640, pad_value=114, want_full=False, out=None):
+    def chain_letterbox(self, frames, params, size=640, pad_value=114, want_full=False, out=None, padding_present=False):
         """Chain + detector input in one call: returns (tensor (N,3,size,size) float16, full-res result or None)."""
+        if padding_present:
+            if out is None:
+                raise ValueError("padding_present needs an `out` buffer prepared with fill_tensor_padding")
+            _check_frames(frames)
+            frames = np.ascontiguousarray(frames)
+            full = None
+            if want_full:
+                full = self._pooled_pinned(frames.shape) if frames.nbytes <= (64 << 20) else np.empty_like(frames)
+            self.submit_io(frames, params, out=full, tensor=out, size=size, pad_value=pad_value, padding_present=True)
+            self.wait()
+            return out, full
         _check_frames(frames)
         frames = np.ascontiguousarray(frames)
         n, h, w, _ = frames.shape

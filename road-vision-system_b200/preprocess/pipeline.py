@@ -223,12 +223,14 @@ class PreprocessPipeline:
 
     # -- new: chain fused with the detector-input stage ------------------------
     def process_batch_to_tensor(self, frames: np.ndarray, size: int = 640, pad_value: int = 114, want_frames: bool = False,
-                                out=None):
+                                out=None, padding_present: bool = False):
         """(B,H,W,3) uint8 -> ((B,3,size,size) float16 network input, processed frames or None).
 
         `out`: optional (B,3,size,size) float16 array for the tensor (pinned, from `Context.pinned_empty(shape, np.float16)`, for
         the overlapped H2D / kernels / D2H pipeline), or "device" to leave the tensor on the GPU (a `DeviceArray`): with pinned
         `frames` the only PCIe traffic is then the upload of the frames.
+        `padding_present=True`: `out` already holds the letterbox padding rows (`Context.fill_tensor_padding`, done once per buffer
+        of a ring), so only the image rows come back over PCIe -- 56 % of the tensor for 1080p frames.
 
         The tensor is what the detector stage builds from `proc` right after the chain (main_preview.py:99 ->
         yolo_ultralytics.py:28-35: letterbox, BGR->RGB, HWC->CHW, /255, half).  When the chain is the stock
@@ -264,4 +266,5 @@ class PreprocessPipeline:
             ctx.submit_io(frames, segs[0], out=full, tensor=dev, size=size, pad_value=pad_value)
             ctx.wait()
             return dev, full
-        return ctx.chain_letterbox(frames, segs[0], size, pad_value, want_full=want_frames, out=out)
+        return ctx.chain_letterbox(frames, segs[0], size, pad_value, want_full=want_frames, out=out,
+                                   padding_present=bool(padding_present and out is not None))

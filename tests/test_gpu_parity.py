@@ -635,3 +635,30 @@ def test_contexts_are_independent_across_threads():
     for t in ts:
         t.join()
     assert not errors, errors
+
+
+def test_tensor_rows_only_download(ctx):
+    """padding_present: a host tensor buffer that already holds the letterbox padding rows gets only its image rows back over PCIe;
+    the complete tensor equals the ordinary one (fused 1080p, unfused ragged, and a portrait frame whose padding is left / right)."""
+    import rvb200
+    from rvb200 import synth
+    cfg = {"chain": [{"name": "CLAHEDehaze", "params": {"space": "YCrCb"}}, {"name": "MedianDerain", "params": {"ksize": 3}}]}
+    pl = rvb200.PreprocessPipeline(cfg, context=ctx)
+    for (h, w) in [(1080, 1920), (539, 961), (640, 360)]:
+        frames = np.stack([synth.road_frame(h, w, 850 + i) for i in range(5)])
+        want, _ = pl.process_batch_to_tensor(frames)
+        buf = ctx.pinned_empty(want.shape, np.float16)
+        buf[:] = 7.0                                                 # poison: rows the copy skips keep whatever the buffer held
+        ctx.fill_tensor_padding(buf, h, w, 640)
+        ctx.set_option("chunk_frames", 2)
+        try:
+            got, _ = pl.process_batch_to_tensor(frames, out=buf, padding_present=True)
+        finally:
+            ctx.set_option("chunk_frames", 0)
+        assert got is buf and np.array_equal(buf.view(np.uint16), want.view(np.uint16)), (h, w)
+        nw, nh, top, left, _ = ctx.letterbox_geometry(h, w, 640)
+        if nh < 640:                                                 # without the pre-fill the padding rows are simply not written
+            buf[:] = 7.0
+            pl.process_batch_to_tensor(frames, out=buf, padding_present=True)
+            assert np.all(buf[:, :, :top, :] == 7.0) and np.all(buf[:, :, top + nh:, :] == 7.0)
+            assert np.array_equal(buf[:, :, top:top + nh, :].view(np.uint16), want[:, :, top:top + nh, :].view(np.uint16))
