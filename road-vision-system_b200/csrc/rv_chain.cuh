@@ -76,6 +76,9 @@ constexpr int A_STRIDE = BOX_W * 3 + 16; // bytes per staged BGR row: the box st
 constexpr int P_STRIDE = BOX_W;        // words per plane row (one u16x2 word per pixel)
 constexpr int O_STRIDE = TILE_W * 3;   // bytes per output staging row
 constexpr int MAXQ = 6;                // quad tables kept in shared memory per CTA
+#ifndef RV_PLANE_SKEW
+#define RV_PLANE_SKEW 24
+#endif
 
 struct ChainArgs {
     const uint8_t *src; size_t spitch, sfstride;
@@ -114,8 +117,15 @@ struct ChainSmem {
     static constexpr int R = K / 2;
     static constexpr int BOX_H = TILE_H + 2 * R;
     static constexpr int NSLOT = HALF + 2 * R;
+    // words between the channel planes.  A skew of 24 makes the plane offset = 24 (mod 32 banks): consecutive median tasks
+    // (group m fastest, then channel) then step through the banks by 6 words ACROSS the change of channel as well, so a half-warp that
+    // straddles two channels' tasks reads 16 distinct even banks with its 8-byte loads instead of colliding two-way (measured on
+    // k_chain<YCrCb,5>: bank-conflict wavefronts 40.8 M -> 28.0 M per 64 frames, +0.2 % fps; <YCrCb,3>: +1.1 %).  Not for LAB: the
+    // 192 extra bytes push k_chain<LAB,3> from three CTAs per SM to two (-7 %).
+    static constexpr int SKEW = (MODE == 1) ? 0 : RV_PLANE_SKEW;
+    static constexpr int PLANE = NSLOT * P_STRIDE + SKEW;
     static constexpr size_t a_bytes = (size_t)BOX_H * A_STRIDE;
-    static constexpr size_t p_bytes = K > 0 ? (size_t)3 * NSLOT * P_STRIDE * 4 : (size_t)TILE_H * O_STRIDE;  // K==0: output staging
+    static constexpr size_t p_bytes = K > 0 ? (size_t)(3 * PLANE - SKEW) * 4 : (size_t)TILE_H * O_STRIDE;  // K==0: output staging
     static constexpr size_t row_bytes = (size_t)BOX_H * 16;
     static constexpr size_t q_bytes = MODE == 2 ? 0 : (size_t)MAXQ * 256 * 4;
     static constexpr size_t t_bytes = MODE == 1 ? sizeof(LabTabs) : MODE == 0 ? sizeof(YccTabs) : 0;
@@ -415,7 +425,6 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
         }
     } else {
         // planes P[c][slot][px]: low half = row `slot`, high half = row `slot + HALF` of the box
-        constexpr int NSLOT = S::NSLOT;
         for (int s = warp; s < HALF; s += CHAIN_WARPS) {
             int o0[12], o1[12];
             compute_row(s, o0);
@@ -427,8 +436,8 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
                 w.y = pack2(o0[4 * c + 1], o1[4 * c + 1]);
                 w.z = pack2(o0[4 * c + 2], o1[4 * c + 2]);
                 w.w = pack2(o0[4 * c + 3], o1[4 * c + 3]);
-                RV_CHECK_IDX(4 * ((c * NSLOT + s) * P_STRIDE + 4 * lane) + 15, S::p_bytes, "P (plane store)");
-                *reinterpret_cast<uint4 *>(P + (c * NSLOT + s) * P_STRIDE + 4 * lane) = w;
+                RV_CHECK_IDX(4 * (c * S::PLANE + s * P_STRIDE + 4 * lane) + 15, S::p_bytes, "P (plane store)");
+                *reinterpret_cast<uint4 *>(P + c * S::PLANE + s * P_STRIDE + 4 * lane) = w;
             }
             if (s < 2 * R) {       // rows [HALF, HALF+2R) are also the low half of slots [HALF, HALF+2R)
                 compute_row(s + TILE_H, o0);
@@ -439,8 +448,8 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
                     w.y = pack2(o1[4 * c + 1], o0[4 * c + 1]);
                     w.z = pack2(o1[4 * c + 2], o0[4 * c + 2]);
                     w.w = pack2(o1[4 * c + 3], o0[4 * c + 3]);
-                    RV_CHECK_IDX(4 * ((c * NSLOT + s + HALF) * P_STRIDE + 4 * lane) + 15, S::p_bytes, "P (tail plane store)");
-                    *reinterpret_cast<uint4 *>(P + (c * NSLOT + s + HALF) * P_STRIDE + 4 * lane) = w;
+                    RV_CHECK_IDX(4 * (c * S::PLANE + (s + HALF) * P_STRIDE + 4 * lane) + 15, S::p_bytes, "P (tail plane store)");
+                    *reinterpret_cast<uint4 *>(P + c * S::PLANE + (s + HALF) * P_STRIDE + 4 * lane) = w;
                 }
             }
         }
@@ -453,7 +462,6 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
     constexpr bool TWO_ROW = (K == 5 && RV_MEDIAN5_2ROW) || (K == 3 && RV_MEDIAN3_2ROW);
     if constexpr (TWO_ROW) {
         // two vertically adjacent output rows per task (slots s, s+1): the K-1 middle window rows are shared
-        constexpr int NSLOT = S::NSLOT;
         constexpr int M = (K == 5) ? RV_MEDIAN5X2_M : RV_MEDIAN3X2_M;
         constexpr int NG = TILE_W / M;
         constexpr int NC = M + K - 1;
@@ -475,7 +483,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             if constexpr (DC + 1 >= 3) { if (c >= 3) { c -= 3; ++sp; } }
             if (!live) continue;
             uint32_t v[NC][NR];
-            const uint32_t *pc = P + (co * NSLOT + s) * P_STRIDE;
+            const uint32_t *pc = P + co * S::PLANE + s * P_STRIDE;
             RV_CHECK_IDX(4 * ((pc - P) + (NR - 1) * P_STRIDE + M * mo + C0 + NC - 1) + 3, S::p_bytes, "P (two-row median load)");
             RV_CHECK_IDX((pc - P) + M * mo + (C0 & ~1), S::p_bytes / 4, "P (two-row median first word)");
             if constexpr (M == 4) {
@@ -526,7 +534,6 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
         }
         __syncthreads();
     } else if constexpr (K > 0) {
-        constexpr int NSLOT = S::NSLOT;
         constexpr int M = MedianCfg<K>::M;
         constexpr int NG = TILE_W / M;               // output groups per row
         constexpr int NC = M + K - 1;                // pixel columns per group
@@ -537,7 +544,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             if (x0 + M * m >= g.W) continue;
             if (y0 + s >= g.H) continue;
             uint32_t v[NC][K];
-            const uint32_t *pc = P + (c * NSLOT + s) * P_STRIDE;
+            const uint32_t *pc = P + c * S::PLANE + s * P_STRIDE;
             constexpr int C0 = LPAD - R;                 // first needed plane word, relative to the group's first output
             RV_CHECK_IDX(4 * ((pc - P) + (K - 1) * P_STRIDE + M * m + C0 + NC - 1) + 3, S::p_bytes, "P (median load)");
             RV_CHECK_IDX((pc - P) + M * m + C0, S::p_bytes / 4, "P (median first word)");
