@@ -128,9 +128,9 @@ __device__ __forceinline__ void lab_inv_tail(const LabTabs *t, int y, int ix, in
     int ro = lab_shr<14>(12615 * x - 6296 * y - 2223 * z + 8192);
     int go = lab_shr<14>(-3773 * x + 7684 * y + 185 * z + 8192);
     int bo = lab_shr<14>(217 * x - 836 * y + 4715 * z + 8192);
-    ro = min(max(ro, 0), 4095);
-    go = min(max(go, 0), 4095);
-    bo = min(max(bo, 0), 4095);
+    ro = __vimin_s32_relu(ro, 4095);                  // clamp to [0, 4095] in one VIMNMX.RELU each
+    go = __vimin_s32_relu(go, 4095);
+    bo = __vimin_s32_relu(bo, 4095);
     B = t->ig[bo];
     G = t->ig[go];
     R = t->ig[ro];

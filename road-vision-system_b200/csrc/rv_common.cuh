@@ -37,7 +37,7 @@ struct Geo {
 #define RV_CHECK_IDX(i, n, what) ((void)0)
 #endif
 
-__device__ __forceinline__ int sat8(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ int sat8(int v) { return __vimin_s32_relu(v, 255); }      // max(min(v, 255), 0): one VIMNMX.RELU
 
 __device__ __forceinline__ int reflect101(int p, int len)
 {

@@ -1,6 +1,7 @@
 #!/bin/bash
 # round 2, call E: full parity suite, latency / fog / config tables, then the ncu captures of the shipped kernels (one GPU)
 mkdir -p gpurun_out
+python -c "import rvb200; print(rvb200.kernel_source_hash())" > gpurun_out/r2e_hash.txt
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2e_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2e_pytest.log
 timeout 600 python tests/perf/bench_latency.py > gpurun_out/r2e_latency.jsonl 2> gpurun_out/r2e_latency.err; echo "latency rc=$?"; cat gpurun_out/r2e_latency.jsonl
 timeout 600 python tests/perf/bench_fog.py > gpurun_out/r2e_fog.json 2> gpurun_out/r2e_fog.err; echo "fog rc=$?"; cat gpurun_out/r2e_fog.json; tail -3 gpurun_out/r2e_fog.err
