@@ -205,3 +205,24 @@ def test_profile_constants_belong_to_the_shipped_kernels():
         assert j["dram_bytes_read"] > 0 and j["warp_instructions"] > 0
     j = json.load(open(os.path.join(ROOT, "profiles", "final_k_chain.json")))
     assert "k_chain<0, 5>" in j["kernel"] and j["grid"] == "(16, 23, 64)"
+
+
+def test_reference_arm_contract():
+    """`bench.py --impl reference` prints one JSON line with the GPU arm's metric / unit / config, `impl: reference`, a cpu_baseline
+    describing the run and an e2e object without copies; it runs the reference's own PreprocessPipeline when oracle/_ref is installed."""
+    import json
+    pytest.importorskip("cv2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    sys.path.insert(0, ROOT)
+    import bench
+    want = bench.base_line(1, 1, 1)
+    for k in ("metric", "unit", "n_gpus", "steps", "warmup", "higher_is_better", "scaling", "dtype", "data", "config"):
+        assert line[k] == want[k], k
+    assert line["impl"] == "reference" and line["gpu_launches"] == 0
+    cb = line["cpu_baseline"]
+    assert cb["value"] == line["value"] > 0 and cb["cores"] >= 1 and cb["unit"] == line["unit"]
+    assert cb["kind"] == ("reference" if os.path.isfile(os.path.join(bench.REF_ROOT, "src", "preprocess", "pipeline.py")) else "port")
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

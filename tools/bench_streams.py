@@ -37,11 +37,14 @@ def main():
 
     def stream(i):
         ctx = rvb200.Context(local)                       # one context (streams + workspaces) per camera stream
-        pipe = rvb200.PreprocessPipeline(cfg)
-        pipe._ctx = lambda: ctx
-        vs = rvb200.VideoSource(reader=SyntheticReader(list(pool), limit=nframes))
+        pipe = rvb200.PreprocessPipeline(cfg, context=ctx)
+        vs = rvb200.VideoSource(reader=SyntheticReader(list(pool), limit=nframes), pinned=None)   # the feeder's ring is the pinned memory
         feeder = rvb200.BatchFeeder(vs, batch=args.batch, shape=(H, W, 3), alloc=ctx.pinned_empty, depth=3, fps=args.fps or None)
         out = ctx.pinned_empty((args.batch, H, W, 3))
+        warm = ctx.pinned_empty((args.batch, H, W, 3))
+        warm[:] = pool[0]
+        for _ in range(3):                                # allocations, tables, graph capture before the camera starts
+            pipe.process_batch(warm, out=out)
         lat, n, t0 = [], 0, time.time()
         for b in feeder:
             pipe.process_batch(b.frames, out=out[:b.count])
