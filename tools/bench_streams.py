@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--fps", type=float, default=30.0)
     ap.add_argument("--seconds", type=float, default=5.0)
     ap.add_argument("--batch", type=int, default=1, help="frames per process_batch call (1 = lowest latency)")
+    ap.add_argument("--skip", type=float, default=2.0, help="seconds at the start of every stream excluded from the statistics")
     args = ap.parse_args()
     import rvb200
     from rvb200 import synth
@@ -45,17 +46,19 @@ def main():
         warm[:] = pool[0]
         for _ in range(3):                                # allocations, tables, graph capture before the camera starts
             pipe.process_batch(warm, out=out)
-        lat, n, t0 = [], 0, time.time()
+        lat, stamps = [], []
         for b in feeder:
             pipe.process_batch(b.frames, out=out[:b.count])
             done = time.time()
             lat.extend(done - b.ts)
-            n += b.count
+            stamps.extend(b.ts)
             feeder.release(b)
-        dt = time.time() - t0
-        lat = np.sort(np.array(lat))
-        results[i] = {"frames": n, "fps": n / dt, "lat_ms_p50": 1e3 * float(lat[len(lat) // 2]), "lat_ms_p99": 1e3 * float(lat[int(len(lat) * 0.99)]),
-                      "lat_ms_max": 1e3 * float(lat[-1])}
+        lat, stamps = np.array(lat), np.array(stamps)
+        keep = stamps >= stamps[0] + args.skip                      # steady state: the first seconds (thread start-up) are excluded
+        lat, st = np.sort(lat[keep]), stamps[keep]
+        span = float(st[-1] - st[0]) if len(st) > 1 else 0.0
+        results[i] = {"frames": int(keep.sum()), "fps": (len(st) - 1) / span if span > 0 else 0.0, "lat_ms_p50": 1e3 * float(lat[len(lat) // 2]),
+                      "lat_ms_p99": 1e3 * float(lat[int(len(lat) * 0.99)]), "lat_ms_max": 1e3 * float(lat[-1])}
 
     threads = [threading.Thread(target=stream, args=(i,)) for i in range(args.streams)]
     t0 = time.time()
@@ -66,7 +69,7 @@ def main():
     wall = time.time() - t0
     print(json.dumps({"config": "C4 1080p streams, chain YCrCb k5", "rank": rank, "gpu": local, "streams": args.streams,
                       "fps_requested": args.fps, "batch": args.batch, "wall_s": round(wall, 2),
-                      "total_fps": round(sum(r["frames"] for r in results) / wall, 1), "per_stream": results}), flush=True)
+                      "excluded_first_s": args.skip, "total_fps": round(sum(r["fps"] for r in results), 1), "per_stream": results}), flush=True)
 
 
 if __name__ == "__main__":
