@@ -6,9 +6,11 @@
 #pragma once
 #include "rv_colour.cuh"
 
-// Median compare-exchange forms.  Plane values are kept as 0x6400|v per 16-bit lane: as unsigned
-// integers they order like v (VIMNMX.U16x2, ALU pipe) and as IEEE halves they are 1024+v, exactly
-// representable together with every difference and sum used below (HFMA2/HADD2, FMA pipe).  On sm_100a both
+// Median compare-exchange forms.  Plane values are kept as 0x00vv per 16-bit lane: as unsigned integers they order like v
+// (VIMNMX.U16x2, ALU pipe) and as IEEE halves they are the subnormals v * 2^-24, exactly representable together with every
+// difference and sum used below (all multiples of 2^-24 below 2^-14; HFMA2/HADD2 on the FMA pipe do not flush them).  (Round 1
+// kept 0x6400|v = 1024 + v instead, switch RV_PLANE_BIASED: the bias cost one more instruction per packed word when the planes
+// are written; without it the headline runs 3.2 % faster, profiles/r2_l_plane_bias.txt.)  On sm_100a both
 // pipes issue 64 lanes/clk/SM (tools/ubench_minmax.cu), so a fraction RV_FMA_NUM/RV_FMA_DEN of the
 // compare-exchanges runs on the FMA pipe:  s = relu(b - a);  max = a + s;  min = b - s.
 #ifndef RV_FMA_NUM
@@ -17,7 +19,13 @@
 #ifndef RV_FMA_DEN
 #define RV_FMA_DEN 1
 #endif
-#define RV_PLANE_BIAS 0x64006400u
+// RV_PLANE_BIASED = 0 keeps the plane values as plain 0x00vv per lane instead: as IEEE halves they are subnormals v * 2^-24, on which
+// the same three operations are still exact (every difference and sum stays a multiple of 2^-24 below 2^-14; no flush-to-zero in
+// fma.rn.relu.f16x2 / add.f16x2), the saturation of two packed values is ONE VIMNMX.S16x2.RELU and no bias has to be attached.
+#ifndef RV_PLANE_BIASED
+#define RV_PLANE_BIASED 0
+#endif
+#define RV_PLANE_BIAS (RV_PLANE_BIASED ? 0x64006400u : 0u)
 #ifndef RV_MEDIAN5_2ROW
 #define RV_MEDIAN5_2ROW 1
 #endif
@@ -78,6 +86,12 @@ constexpr int O_STRIDE = TILE_W * 3;   // bytes per output staging row
 constexpr int MAXQ = 6;                // quad tables kept in shared memory per CTA
 #ifndef RV_PLANE_SKEW
 #define RV_PLANE_SKEW 24
+#endif
+#ifndef RV_DP2A_INDEX
+#define RV_DP2A_INDEX 1                // YCrCb: Y is consumed as the upper half-word of the scaled luminance sum by IDP.2A.HI (table addresses
+#endif                                 // base +- 4 Y in one FMA-pipe instruction, no shift); 0 = shift Y out and add
+#ifndef RV_DP4A_ADDR
+#define RV_DP4A_ADDR 1                 // table addresses from the packed pixel word with IDP.4A (FMA pipe); 0 = byte extraction + add
 #endif
 
 struct ChainArgs {
@@ -262,8 +276,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            qxl[j] -= qx_lo;
-            qcol[j] = qxl[j] << 8;
+            qcol[j] = (qxl[j] - qx_lo) << 10;      // byte offset of the quad column's table; only this form stays live
         }
         for (int ry = tid; ry < BOX_H; ry += CHAIN_THREADS) {
             const int gy = min(max(y0 - R + ry, 0), g.H - 1);
@@ -272,7 +285,8 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             const float ya = __fsub_rn(tyf, fl);
             const int qy = (int)fl + 1;
             RV_CHECK_IDX(ry, BOX_H, "rowp");
-            rowp[ry] = make_float4(ya, __fsub_rn(1.0f, ya), __int_as_float(q_smem ? (((qy - qy_lo) * nqx) << 8) : qy),
+            // .z: shared-memory byte address of the row's first quad table (tables in shared memory), or the global quad row
+            rowp[ry] = make_float4(ya, __fsub_rn(1.0f, ya), __int_as_float(q_smem ? (int)(smem_u32(Qs) + (((qy - qy_lo) * nqx) << 10)) : qy),
                                    __int_as_float((gy - (y0 - R)) * A_STRIDE));
         }
         if (MODE == 1) copy_lab_tabs(const_cast<LabTabs *>(tabs));
@@ -291,6 +305,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
     // packed u16x2 plane words (two values per VIMNMX.S16x2) instead of per value; LAB / passthrough values are exact.
     constexpr bool RAW = (MODE == 0) && (K > 0);
     const uint32_t ycc_s = smem_u32(smem + S::off_t);            // shared-memory address of the chroma tables (MODE 0)
+    [[maybe_unused]] const uint32_t lab_s = ycc_s;              // ... of the LAB tables (MODE 1): same slot
     // phase 1 is instantiated twice (quad tables in shared memory / fetched from global) and the CTA-uniform choice is
     // made once, outside: a predicated dual path costs issue slots for every masked-off address instruction.
     auto phase1 = [&](auto QS) {
@@ -335,31 +350,59 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
         }
         const float ya = rp.x, ya1 = rp.y;
         int ly[4], lx[4], lz[4];                                 // LAB: y and the two XZ arguments of the four pixels
-        const int qrow = __float_as_int(rp.z);                    // (local quad row * quads per row) << 8, or the global row
+        const int qrow = __float_as_int(rp.z);                    // byte address of the row's quad tables in shared memory, or the global row
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int L, c1 = 0, c2 = 0;
-            uint32_t eB = 0, eR = 0;
+            [[maybe_unused]] uint32_t eB = 0, eR = 0, acc = 0;
             if (MODE == 1) {
+#if RV_DP4A_ADDR
+                lab_fwd_px(tabs, lab_s, px[j], L, c1, c2);
+#else
                 lab_fwd(tabs, Bv[j], Gv[j], Rv[j], L, c1, c2);
+#endif
             } else {
                 // A.1 forward: Y from the packed pixel word; the chroma round trip comes from the tables (see YccTabs):
                 // entries of d = B - Y and d = R - Y
-                L = (int)luma_y(px[j]);
                 // one shared term (table base - 4 Y) for both look-ups; the empty asm keeps the compiler from re-associating it
                 // into a subtraction per channel.  The tables are constant after the barrier above and the address depends on
                 // this pixel, so a plain (non-volatile) shared load is safe.
+#if RV_DP2A_INDEX
+                // Y stays inside the scaled sum (its upper half-word): base - 4 Y is one IDP.2A.HI with the byte -4, no shift
+                acc = luma_acc16(px[j]);
+                L = (int)(acc >> 16);                             // only the global-table path and the debug checks use it
+                uint32_t yrow = (uint32_t)__dp2a_hi((int)acc, (int)0xFC000000u, (int)(ycc_s + 4u * 255u));
+#else
+                L = (int)luma_y(px[j]);
                 uint32_t yrow = ycc_s + 4u * 255u - 4u * (uint32_t)L;
+#endif
                 asm("" : "+r"(yrow));
+                // table addresses yrow + 4 B and yrow + 4 R straight from the packed pixel word with one byte dot product each
+                // (IDP.4A, FMA pipe: selects the byte, scales it by the entry size and adds the base) instead of a byte extraction
+                // and a shift-and-add on the ALU pipe, which is the busier one in this kernel
+#if RV_DP4A_ADDR
+                asm("ld.shared.u32 %0, [%1];" : "=r"(eB) : "r"(__dp4a(px[j], 0x00000004u, yrow)));
+                asm("ld.shared.u32 %0, [%1+2048];" : "=r"(eR) : "r"(__dp4a(px[j], 0x00040000u, yrow)));
+#else
                 asm("ld.shared.u32 %0, [%1];" : "=r"(eB) : "r"(yrow + 4u * (uint32_t)Bv[j]));
                 asm("ld.shared.u32 %0, [%1+2048];" : "=r"(eR) : "r"(yrow + 4u * (uint32_t)Rv[j]));
+#endif
             }
             uint32_t q;
-            if constexpr (q_in_smem) RV_CHECK_IDX(qrow + qcol[j] + L, MAXQ * 256, "Qs (LUT quad load)");
-            if constexpr (MODE == 0) RV_CHECK_IDX(255 - L + Bv[j], 512, "ycc table (B - Y)");
-            if constexpr (MODE == 0) RV_CHECK_IDX(255 - L + Rv[j], 512, "ycc table (R - Y)");
-            if constexpr (q_in_smem) q = Qs[qrow + qcol[j] + L];
-            else q = __ldg(qglob + (((size_t)qrow * (g.grid + 1) + (qxl[j] + qx_lo)) << 8) + L);
+            if constexpr (q_in_smem) RV_CHECK_IDX(((qrow + qcol[j]) - (int)smem_u32(Qs)) / 4 + L, MAXQ * 256, "Qs (LUT quad load)");
+            if constexpr (MODE == 0) RV_CHECK_IDX(255 - L + (int)(px[j] & 255), 512, "ycc table (B - Y)");
+            if constexpr (MODE == 0) RV_CHECK_IDX(255 - L + (int)((px[j] >> 16) & 255), 512, "ycc table (R - Y)");
+            if constexpr (q_in_smem) {
+                // entry L of the quad table at byte address qrow + qcol[j]
+#if RV_DP2A_INDEX
+                if constexpr (MODE == 0) asm("ld.shared.u32 %0, [%1];" : "=r"(q) : "r"(__dp2a_hi(acc, 0x04000000u, (uint32_t)(qrow + qcol[j]))));
+                else asm("ld.shared.u32 %0, [%1];" : "=r"(q) : "r"((uint32_t)(qrow + qcol[j]) + 4u * (uint32_t)L));
+#else
+                asm("ld.shared.u32 %0, [%1];" : "=r"(q) : "r"((uint32_t)(qrow + qcol[j]) + 4u * (uint32_t)L));
+#endif
+            } else {
+                q = __ldg(qglob + (((size_t)qrow * (g.grid + 1) + ((qcol[j] >> 10) + qx_lo)) << 8) + L);
+            }
             // 0x4B0000vv = 2^23 + vv ; fma(2^23 + v, w, -2^23 * w) == v * w rounded once (A.3: no FMA contraction
             // between the products and the sums -- each step below is individually rounded)
             const float m00 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7440));
@@ -377,7 +420,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             // RAW: the bias 0x6400 rides along in the magic constant and the float's upper bits are left in place; only the
             // low 16 bits of the sums below are ever used (pack2 keeps the low halves), so no masking is needed.
             // YCrCb: - 256 because the tables' f fields and the G sum carry + 256.
-            constexpr float MAGIC = 12582912.0f + (RAW ? 25600.0f : 0.0f) - (MODE == 0 ? 256.0f : 0.0f);
+            constexpr float MAGIC = 12582912.0f + ((RAW && RV_PLANE_BIASED) ? 25600.0f : 0.0f) - (MODE == 0 ? 256.0f : 0.0f);
             const int Lw = __float_as_int(__fadd_rn(res, MAGIC));
             if (MODE == 1) {
                 lab_inv_args(tabs, Lw & 0x1FF, c1, c2, ly[j], lx[j], lz[j]);
@@ -405,8 +448,13 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
     // two rows' values of one pixel/channel -> one plane word (low half = first row), saturated and biased
     auto pack2 = [&](int lo, int hi) -> uint32_t {
         const uint32_t w = __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
+#if RV_PLANE_BIASED
         if (RAW) return __vmins2(__vmaxs2(w, RV_PLANE_BIAS), RV_PLANE_BIAS | 0x00FF00FFu);
         return w | RV_PLANE_BIAS;
+#else
+        if (RAW) return __vimin_s16x2_relu(w, 0x00FF00FFu);       // max(min(v, 255), 0) on both halves at once
+        return w;
+#endif
     };
 
     if constexpr (K == 0) {

@@ -7,6 +7,8 @@
 #include "rv_common.cuh"
 #include "rv_lab_tables.h"
 
+#include <stddef.h>
+
 namespace rv {
 
 
@@ -40,6 +42,16 @@ __device__ __forceinline__ uint32_t luma_y(uint32_t px)
 {
     constexpr uint32_t CBG = 1868u | (9617u << 16), CR0 = 4899u;
     return __dp2a_hi(CR0, px, __dp2a_lo(CBG, px, 8192u)) >> 14;
+}
+
+// The same sum scaled by four, not shifted: acc = 4 (1868 B + 9617 G + 4899 R) + 32768, so that Y is exactly the UPPER HALF-WORD
+// of acc ((x + 8192) >> 14 == (4 x + 32768) >> 16; acc < 2^24).  A consumer can then take Y straight out of acc with another
+// 16-bit x 8-bit dot product (IDP.2A.HI multiplies the upper half-word by a byte and adds a base): table addresses that are
+// base + 4 Y or base - 4 Y cost one FMA-pipe instruction and the shift that would isolate Y never happens.
+__device__ __forceinline__ uint32_t luma_acc16(uint32_t px)
+{
+    constexpr uint32_t CBG = 7472u | (38468u << 16), CR0 = 19596u;
+    return __dp2a_hi(CR0, px, __dp2a_lo(CBG, px, 32768u));
 }
 
 // A.1 forward
@@ -103,6 +115,24 @@ __device__ __forceinline__ void lab_fwd(const LabTabs *t, int B, int G, int R, i
     a = lab_shr<15>(500 * (fX - fY) + ((128 << 15) + 16384));
     bb = lab_shr<15>(200 * (fY - fZ) + ((128 << 15) + 16384));
 }
+// The same from the packed pixel word (B, G, R, x): the three gamma look-ups take their shared-memory addresses g8 + 2 B / 2 G / 2 R
+// from one byte dot product each (IDP.4A, FMA pipe) instead of a byte extraction plus an add on the ALU pipe.  `tabs_s` is the
+// shared-memory address of `t` (LabTabs::g8 sits at offset 0).
+__device__ __forceinline__ void lab_fwd_px(const LabTabs *t, uint32_t tabs_s, uint32_t px, int &L, int &a, int &bb)
+{
+    uint32_t r, g, b;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(b) : "r"(__dp4a(px, 0x00000002u, tabs_s)));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(g) : "r"(__dp4a(px, 0x00000200u, tabs_s)));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(__dp4a(px, 0x00020000u, tabs_s)));
+    const int fX = t->cb[lab_shr<12>(1777 * (int)r + 1541 * (int)g + 778 * (int)b + 2048)];
+    const int fY = t->cb[lab_shr<12>(871 * (int)r + 2929 * (int)g + 296 * (int)b + 2048)];
+    const int fZ = t->cb[lab_shr<12>(73 * (int)r + 448 * (int)g + 3575 * (int)b + 2048)];
+    L = lab_shr<15>(296 * fY - 1336934 + 16384);
+    a = lab_shr<15>(500 * (fX - fY) + ((128 << 15) + 16384));
+    bb = lab_shr<15>(200 * (fY - fZ) + ((128 << 15) + 16384));
+}
+static_assert(offsetof(LabTabs, g8) == 0, "lab_fwd_px addresses g8 at the start of LabTabs");
+
 __device__ __forceinline__ int lab_xz(int i)
 {
     const int lin = (i * 108) / 841 - 290;            // truncating division, as in C
