@@ -90,6 +90,9 @@ constexpr int MAXQ = 6;                // quad tables kept in shared memory per 
 #ifndef RV_DP2A_INDEX
 #define RV_DP2A_INDEX 1                // YCrCb: Y is consumed as the upper half-word of the scaled luminance sum by IDP.2A.HI (table addresses
 #endif                                 // base +- 4 Y in one FMA-pipe instruction, no shift); 0 = shift Y out and add
+#ifndef RV_I2F_BLEND
+#define RV_I2F_BLEND 2                 // bit 0: YCrCb kernels, bit 1: LAB kernels take the I2F form of the blend's byte -> float step
+#endif
 #ifndef RV_DP4A_ADDR
 #define RV_DP4A_ADDR 1                 // table addresses from the packed pixel word with IDP.4A (FMA pipe); 0 = byte extraction + add
 #endif
@@ -405,14 +408,24 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             }
             // 0x4B0000vv = 2^23 + vv ; fma(2^23 + v, w, -2^23 * w) == v * w rounded once (A.3: no FMA contraction
             // between the products and the sums -- each step below is individually rounded)
-            const float m00 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7440));
-            const float m01 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7441));
-            const float m10 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7442));
-            const float m11 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7443));
-            const float p00 = __fmaf_rn(m00, xa1[j], cxa1[j]);
-            const float p01 = __fmaf_rn(m01, xa[j], cxa[j]);
-            const float p10 = __fmaf_rn(m10, xa1[j], cxa1[j]);
-            const float p11 = __fmaf_rn(m11, xa[j], cxa[j]);
+            float p00, p01, p10, p11;
+            if constexpr (MODE == 1 ? (RV_I2F_BLEND & 2) != 0 : (RV_I2F_BLEND & 1) != 0) {
+                // bytes -> floats with I2F.U8 (byte selector; conversion unit, off the ALU pipe) and plain multiplies.  Pays in the LAB
+                // kernels, whose ALU pipe is the binding one (+0.5 % k3, +1.2 % k5); costs 1.1 % in k_chain<YCrCb,5>.
+                p00 = __fmul_rn((float)(q & 255u), xa1[j]);
+                p01 = __fmul_rn((float)((q >> 8) & 255u), xa[j]);
+                p10 = __fmul_rn((float)((q >> 16) & 255u), xa1[j]);
+                p11 = __fmul_rn((float)(q >> 24), xa[j]);
+            } else {
+                const float m00 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7440));
+                const float m01 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7441));
+                const float m10 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7442));
+                const float m11 = __uint_as_float(__byte_perm(q, 0x4B000000u, 0x7443));
+                p00 = __fmaf_rn(m00, xa1[j], cxa1[j]);
+                p01 = __fmaf_rn(m01, xa[j], cxa[j]);
+                p10 = __fmaf_rn(m10, xa1[j], cxa1[j]);
+                p11 = __fmaf_rn(m11, xa[j], cxa[j]);
+            }
             const float top = __fmul_rn(__fadd_rn(p00, p01), ya1);
             const float bot = __fmul_rn(__fadd_rn(p10, p11), ya);
             const float res = __fadd_rn(top, bot);
