@@ -90,6 +90,9 @@ constexpr int MAXQ = 6;                // quad tables kept in shared memory per 
 #ifndef RV_DP2A_INDEX
 #define RV_DP2A_INDEX 1                // YCrCb: Y is consumed as the upper half-word of the scaled luminance sum by IDP.2A.HI (table addresses
 #endif                                 // base +- 4 Y in one FMA-pipe instruction, no shift); 0 = shift Y out and add
+#ifndef RV_LAB_DP2A
+#define RV_LAB_DP2A 1                  // LAB: every table index is the upper (or lower) half-word of a scaled sum, consumed by IDP.2A (FMA pipe)
+#endif
 #ifndef RV_I2F_BLEND
 #define RV_I2F_BLEND 2                 // bit 0: YCrCb kernels, bit 1: LAB kernels take the I2F form of the blend's byte -> float step
 #endif
@@ -359,7 +362,10 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             int L, c1 = 0, c2 = 0;
             [[maybe_unused]] uint32_t eB = 0, eR = 0, acc = 0;
             if (MODE == 1) {
-#if RV_DP4A_ADDR
+#if RV_LAB_DP2A
+                lab_fwd_px2(lab_s, px[j], acc, c1, c2);
+                L = (int)(acc >> 16);                             // only the global-table path and the debug checks use it
+#elif RV_DP4A_ADDR
                 lab_fwd_px(tabs, lab_s, px[j], L, c1, c2);
 #else
                 lab_fwd(tabs, Bv[j], Gv[j], Rv[j], L, c1, c2);
@@ -398,7 +404,8 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             if constexpr (q_in_smem) {
                 // entry L of the quad table at byte address qrow + qcol[j]
 #if RV_DP2A_INDEX
-                if constexpr (MODE == 0) asm("ld.shared.u32 %0, [%1];" : "=r"(q) : "r"(__dp2a_hi(acc, 0x04000000u, (uint32_t)(qrow + qcol[j]))));
+                if constexpr (MODE == 0 || (MODE == 1 && RV_LAB_DP2A))
+                    asm("ld.shared.u32 %0, [%1];" : "=r"(q) : "r"(__dp2a_hi(acc, 0x04000000u, (uint32_t)(qrow + qcol[j]))));
                 else asm("ld.shared.u32 %0, [%1];" : "=r"(q) : "r"((uint32_t)(qrow + qcol[j]) + 4u * (uint32_t)L));
 #else
                 asm("ld.shared.u32 %0, [%1];" : "=r"(q) : "r"((uint32_t)(qrow + qcol[j]) + 4u * (uint32_t)L));
@@ -436,7 +443,11 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             constexpr float MAGIC = 12582912.0f + ((RAW && RV_PLANE_BIASED) ? 25600.0f : 0.0f) - (MODE == 0 ? 256.0f : 0.0f);
             const int Lw = __float_as_int(__fadd_rn(res, MAGIC));
             if (MODE == 1) {
+#if RV_LAB_DP2A
+                lab_inv_args_w(lab_s, (uint32_t)Lw, c1, c2, ly[j], lx[j], lz[j]);
+#else
                 lab_inv_args(tabs, Lw & 0x1FF, c1, c2, ly[j], lx[j], lz[j]);
+#endif
             } else {
                 // A.1 inverse: B' = Y' + fB, G' = Y' + ((tB + tR + 8192) >> 14), R' = Y' + fR
                 const int L2 = RAW ? Lw : (Lw << 16) >> 16;          // non-RAW: sign-extended Y' - 256

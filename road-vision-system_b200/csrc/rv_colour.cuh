@@ -133,6 +133,42 @@ __device__ __forceinline__ void lab_fwd_px(const LabTabs *t, uint32_t tabs_s, ui
 }
 static_assert(offsetof(LabTabs, g8) == 0, "lab_fwd_px addresses g8 at the start of LabTabs");
 
+// Same results with every table index taken as the UPPER HALF-WORD of a scaled sum by IDP.2A.HI (FMA pipe) -- no shift and no address
+// add on the ALU pipe, which is the binding one in k_chain<LAB,*>: the matrix rows are scaled by 16 (index = (16 (row . rgb + 2048)) >> 16,
+// coefficients <= 57200 still fit 16 bits... they are ordinary IMAD immediates here; sums < 2^28), the L formula by 2.  L itself is returned
+// inside accL (L = accL >> 16) so that the caller's quad-table address can be formed the same way.
+__device__ __forceinline__ void lab_fwd_px2(uint32_t tabs_s, uint32_t px, uint32_t &accL, int &a, int &bb)
+{
+    uint32_t r, g, b, fX, fY, fZ;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(b) : "r"(__dp4a(px, 0x00000002u, tabs_s)));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(g) : "r"(__dp4a(px, 0x00000200u, tabs_s)));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(__dp4a(px, 0x00020000u, tabs_s)));
+    const uint32_t cb_s = tabs_s + (uint32_t)offsetof(LabTabs, cb);
+    const uint32_t sx = 28432u * r + 24656u * g + 12448u * b + 32768u;        // 16 x (1777 r + 1541 g + 778 b + 2048)
+    const uint32_t sy = 13936u * r + 46864u * g + 4736u * b + 32768u;         // 16 x (871 r + 2929 g + 296 b + 2048)
+    const uint32_t sz = 1168u * r + 7168u * g + 57200u * b + 32768u;          // 16 x (73 r + 448 g + 3575 b + 2048)
+    asm("ld.shared.u16 %0, [%1];" : "=r"(fX) : "r"(__dp2a_hi(sx, 0x02000000u, cb_s)));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(fY) : "r"(__dp2a_hi(sy, 0x02000000u, cb_s)));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(fZ) : "r"(__dp2a_hi(sz, 0x02000000u, cb_s)));
+    accL = 592u * fY - 2641100u;                                              // 2 x (296 fY - 1336934 + 16384) >= 0
+    a = lab_shr<15>(500 * ((int)fX - (int)fY) + ((128 << 15) + 16384));
+    bb = lab_shr<15>(200 * ((int)fY - (int)fZ) + ((128 << 15) + 16384));
+}
+
+// A.2 inverse arguments from the rounded blend result as it leaves the float unit: Lw = bits of (res + 1.5 * 2^23), i.e. the new L in
+// the low half-word under a constant upper half; the two look-ups take base + 2 L from one IDP.2A.LO each.
+__device__ __forceinline__ void lab_inv_args_w(uint32_t tabs_s, uint32_t Lw, int a, int b, int &y, int &ix, int &iz)
+{
+    uint32_t yy, fy;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(yy) : "r"(__dp2a_lo(Lw, 0x00000002u, tabs_s + (uint32_t)offsetof(LabTabs, yt))));
+    asm("ld.shared.u16 %0, [%1];" : "=r"(fy) : "r"(__dp2a_lo(Lw, 0x00000002u, tabs_s + (uint32_t)offsetof(LabTabs, ft))));
+    y = (int)yy;
+    const int adiv = lab_shr<13>(5 * a * 53687 + 128) - 4194;
+    const int bdiv = lab_shr<9>(b * 41943 + 16) - 10485 + 1;
+    ix = (int)fy + adiv;
+    iz = (int)fy - bdiv;
+}
+
 __device__ __forceinline__ int lab_xz(int i)
 {
     const int lin = (i * 108) / 841 - 290;            // truncating division, as in C
