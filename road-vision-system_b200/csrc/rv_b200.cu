@@ -29,7 +29,10 @@ using namespace rv;
 
 namespace {
 
-constexpr int NPIPE = 3;
+#ifndef RV_NPIPE
+#define RV_NPIPE 3
+#endif
+constexpr int NPIPE = RV_NPIPE;          // streams (and buffer sets) of the chunked host pipeline
 constexpr int NWS = NPIPE + 3;               // workspace sets: [0, NPIPE) host pipeline, NPIPE / NPIPE+1 device path, NPIPE+2 single-frame path
 constexpr int WS_FRAME = NPIPE + 2;
 
