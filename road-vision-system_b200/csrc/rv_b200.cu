@@ -88,7 +88,7 @@ struct FrameGraph {
     long kernels = 0;                       // kernel nodes in the graph (launch accounting)
 };
 
-struct Buf_host_fwd {
+struct HostBuf {
     uint8_t *p = nullptr;
     size_t cap = 0;
 };
@@ -178,7 +178,7 @@ struct rv_ctx {
     void *fog = nullptr;                    // state of rv_fog.cu (fog synthesis), destroyed through fog_destroy
     void (*fog_destroy)(void *) = nullptr;
     StagePool *stage = nullptr;             // helper threads + page-locked staging frame for pageable single-frame input
-    Buf_host_fwd fstage;                    // (declared below) page-locked staging frame
+    HostBuf fstage;                         // page-locked staging frame of the optional helper-thread upload
     long stage_threads = 0;                 // option "stage_threads": helpers next to the caller; 0 (default) = the driver stages pageable
                                             // input itself, which measured 2x faster on B200 hosts (0.47 ms against 0.95 ms per 1080p call)
     long frame_graphs = 1;                  // option "frame_graphs": 0 = the single-frame path launches directly (no CUDA graph)
