@@ -80,7 +80,8 @@ def build_library(force=False, verbose=False):
     return _SO
 
 
-KERNEL_SOURCES = ("Makefile", "rv_common.cuh", "rv_colour.cuh", "rv_hist_lut.cuh", "rv_chain.cuh", "rv_median_net.h", "rv_lab_tables.h")
+KERNEL_SOURCES = ("Makefile", "rv_common.cuh", "rv_colour.cuh", "rv_hist_lut.cuh", "rv_chain.cuh", "rv_median_net.h", "rv_lab_tables.h",
+                  "rv_ycc_g.h")
 
 
 def kernel_source_hash():

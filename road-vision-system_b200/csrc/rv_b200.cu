@@ -24,6 +24,7 @@
 
 #include "rv_kernels.cuh"
 #include "rv_internal.h"
+#include "rv_ycc_g.h"
 
 using namespace rv;
 
@@ -216,9 +217,14 @@ void build_ycc_table(YccTabs &y)
         const int cb = clamp8((d * 9241 + ((128 << 14) + 8192)) >> 14) - 128;
         const int cr = clamp8((d * 11682 + ((128 << 14) + 8192)) >> 14) - 128;
         const int fB = (cb * 29049 + 8192) >> 14, fR = (cr * 22987 + 8192) >> 14;
+#if RV_YCC16
+        y.e[i] = ((uint32_t)RV_YCC_GB[cb + 128] << 16) | (uint32_t)(fB + 256);
+        y.e[512 + i] = ((uint32_t)RV_YCC_GR[cr + 128] << 16) | (uint32_t)(fR + 256);
+#else
         const int tB = cb * -5636 / 2, tR = cr * -11698 / 2 + 4096 + (1 << 21);      // both products are even
         y.e[i] = ((uint32_t)(fB + 256) << 22) | ((uint32_t)tB & 0x3FFFFFu);
         y.e[512 + i] = ((uint32_t)(fR + 256) << 22) | ((uint32_t)tR & 0x3FFFFFu);
+#endif
     }
 }
 

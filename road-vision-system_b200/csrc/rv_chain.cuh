@@ -449,13 +449,23 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
                 lab_inv_args(tabs, Lw & 0x1FF, c1, c2, ly[j], lx[j], lz[j]);
 #endif
             } else {
-                // A.1 inverse: B' = Y' + fB, G' = Y' + ((tB + tR + 8192) >> 14), R' = Y' + fR
+                // A.1 inverse: B' = Y' + fB, G' = Y' + ((tB + tR + 8192) >> 14), R' = Y' + fR  (table layout: rv_colour.cuh, YccTabs)
+#if RV_YCC16
+                // the f terms sit in the low half-words, so plain adds give B' and R' in their low 16 bits (the upper bits are never
+                // used: pack2 keeps the low halves); the G term is the top nine bits of the sum of the two entries
+                const int bb = Lw + (int)eB;
+                const int gg = Lw + (int)((eB + eR) >> 23);
+                const int rr = Lw + (int)eR;
+                if (RAW) { o[j] = bb; o[4 + j] = gg; o[8 + j] = rr; }
+                else { o[j] = sat8((int)(short)bb); o[4 + j] = sat8((int)(short)gg); o[8 + j] = sat8((int)(short)rr); }
+#else
                 const int L2 = RAW ? Lw : (Lw << 16) >> 16;          // non-RAW: sign-extended Y' - 256
                 const int bb = L2 + (int)(eB >> 22);
                 const int gg = L2 + (int)(((eB + eR) << 10) >> 23);
                 const int rr = L2 + (int)(eR >> 22);
                 if (RAW) { o[j] = bb; o[4 + j] = gg; o[8 + j] = rr; }
                 else { o[j] = sat8(bb); o[4 + j] = sat8(gg); o[8 + j] = sat8(rr); }
+#endif
             }
         }
         if (MODE == 1) {

@@ -28,10 +28,18 @@ __device__ LabTabs g_lab;   // filled once per context from rv_lab_tables.h
 // YCrCb chroma round trip (A.1) as two 511-entry tables indexed by d + 255, d = B - Y (first 512 words) or R - Y (next 512).
 // Cb and Cr only pass through the CLAHE, so B' = Y' + fB(d_B), R' = Y' + fR(d_R) and G' = Y' + ((tB + tR + 8192) >> 14) with
 //   fB = ((Cb - 128) * 29049 + 8192) >> 14,  tB = (Cb - 128) * -5636   (Cb = sat8((d * 9241 + (128 << 14) + 8192) >> 14)),
-//   fR = ((Cr - 128) * 22987 + 8192) >> 14,  tR = (Cr - 128) * -11698  (Cr likewise with 11682);  tB, tR and 8192 are even.
-// Entry: bits 22..31 = f + 256, bits 0..21 = t / 2 modulo 2^22 (+ 4096 + 2^21 in the R table, so that the sum of the two
-// fields lies in [0, 2^22)): ((eB + eR) << 10) >> 23 == 256 + ((tB + tR + 8192) >> 14), e >> 22 == f + 256 -- a shift-and-add
-// (LEA.HI) per channel.  Built on the host (rv_b200.cu: build_ycc_table) with the same integer formulas.
+//   fR = ((Cr - 128) * 22987 + 8192) >> 14,  tR = (Cr - 128) * -11698  (Cr likewise with 11682).
+// RV_YCC16 = 1 (round 2).  Entry: low half-word = f + 256 (in [29, 481]: the two low halves add without a carry), high half-word =
+// the 16-bit G term of rv_ycc_g.h (seven fractional bits; (gB + gR) >> 7 == 256 + ((tB + tR + 8192) >> 14) EXACTLY for all 65,536
+// chroma pairs, tools/gen_ycc_g_tables.py).  With s = eB + eR:  G' = Y' + (s >> 23) - 256 is one LEA.HI, and B' = Y' + eB,
+// R' = Y' + eR are plain adds whose LOW 16 BITS are the result (+ 256): three adds and one shift-add instead of six instructions,
+// and only one of them on the ALU pipe instead of four.
+// RV_YCC16 = 0 (round 1).  Entry: bits 22..31 = f + 256, bits 0..21 = t / 2 modulo 2^22 (+ 4096 + 2^21 in the R table):
+// ((eB + eR) << 10) >> 23 == 256 + ((tB + tR + 8192) >> 14), e >> 22 == f + 256.
+// Built on the host (rv_b200.cu: build_ycc_table) with the same integer formulas; checked over all 2^24 colours by the CPU suite.
+#ifndef RV_YCC16
+#define RV_YCC16 1
+#endif
 struct YccTabs { uint32_t e[1024]; };
 __device__ YccTabs g_ycc;
 

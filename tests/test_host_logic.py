@@ -184,13 +184,20 @@ def test_ycc_chroma_table_equals_oracle_round_trip_exhaustive():
     Y = ycc[..., 0].astype(np.int64)
     eB = tab[:512][img[..., 0].astype(np.int64) - Y + 255].astype(np.int64)
     eR = tab[512:][img[..., 2].astype(np.int64) - Y + 255].astype(np.int64)
-    fB, fR = (eB >> 22) - 256, (eR >> 22) - 256
-    g = ((((eB + eR) & 0xFFFFFFFF) << 10) & 0xFFFFFFFF) >> 23
+    # layout of round 2 (csrc/rv_colour.cuh, RV_YCC16): low half-word f + 256, high half-word the 16-bit G term of rv_ycc_g.h
+    fB, fR = (eB & 0xFFFF) - 256, (eR & 0xFFFF) - 256
+    assert ((eB & 0xFFFF) + (eR & 0xFFFF)).max() < 65536 and ((eB >> 16) + (eR >> 16)).max() < 65536      # no carries between the fields
+    g = ((eB + eR) & 0xFFFFFFFF) >> 23
     for shift in (0, 1, 37, 128, 255):           # Y' = (Y + shift) mod 256 exercises every (Y', chroma) pairing that matters
         y2 = (Y + shift) & 255
         want = O.ycrcb2bgr(np.stack([y2.astype(np.uint8), ycc[..., 1], ycc[..., 2]], -1))
         got = np.stack([np.clip(y2 + fB, 0, 255), np.clip(y2 + g - 256, 0, 255), np.clip(y2 + fR, 0, 255)], -1).astype(np.uint8)
         assert np.array_equal(got, want), shift
+
+
+def test_ycc_g_tables_are_current_and_exact():
+    """csrc/rv_ycc_g.h is what tools/gen_ycc_g_tables.py generates (the script re-solves and re-verifies all 65,536 chroma pairs)."""
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_ycc_g_tables.py"), "--check"], stdout=subprocess.DEVNULL, timeout=600)
 
 
 def test_profile_constants_belong_to_the_shipped_kernels():
