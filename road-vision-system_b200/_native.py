@@ -86,13 +86,22 @@ KERNEL_SOURCES = ("Makefile", "rv_common.cuh", "rv_colour.cuh", "rv_hist_lut.cuh
 
 def kernel_source_hash():
     """SHA-256 (first 16 hex digits) over the files that determine the device code of the chain's kernels (not the host-side
-    C ABI).  profiles/final_*.json records it with every ncu capture; bench.py and the CPU test suite compare it with the tree,
-    so profile-derived constants can never silently outlive the code they were measured on."""
+    C ABI), with comments and white space removed -- so that editing a comment does not orphan a profile, while any change a
+    compiler could see does.  profiles/final_*.json records it with every ncu capture; bench.py and the CPU test suite compare it
+    with the tree, so profile-derived constants can never silently outlive the code they were measured on."""
     import hashlib
+    import re
     h = hashlib.sha256()
     for name in KERNEL_SOURCES:
-        with open(os.path.join(_CSRC, name), "rb") as fh:
-            h.update(name.encode() + b"\0" + fh.read() + b"\0")
+        with open(os.path.join(_CSRC, name), "r") as fh:
+            text = fh.read()
+        if name != "Makefile":
+            text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)           # block comments
+            text = re.sub(r"//[^\n]*", " ", text)                        # line comments (no string in these files contains //)
+        else:
+            text = re.sub(r"#[^\n]*", " ", text)
+        text = " ".join(text.split())
+        h.update(name.encode() + b"\0" + text.encode() + b"\0")
     return h.hexdigest()[:16]
 
 

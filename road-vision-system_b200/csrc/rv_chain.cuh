@@ -307,8 +307,8 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
 
     // ---- phase 1: CLAHE on the luminance of every staged pixel (or plain unpack when MODE == 2)
     const uint32_t *qglob = (MODE != 2) ? a.quads + (size_t)f * (g.grid + 1) * (g.grid + 1) * 256 : nullptr;
-    // YCrCb results are produced UNCLAMPED with RV_BIAS16 added (K > 0): the saturation to [0,255] happens on the
-    // packed u16x2 plane words (two values per VIMNMX.S16x2) instead of per value; LAB / passthrough values are exact.
+    // YCrCb results are produced UNCLAMPED (K > 0): the saturation to [0,255] happens on the packed u16x2 plane words
+    // (two values per VIMNMX.S16x2.RELU) instead of per value; LAB / passthrough values are exact.
     constexpr bool RAW = (MODE == 0) && (K > 0);
     const uint32_t ycc_s = smem_u32(smem + S::off_t);            // shared-memory address of the chroma tables (MODE 0)
     [[maybe_unused]] const uint32_t lab_s = ycc_s;              // ... of the LAB tables (MODE 1): same slot
@@ -437,7 +437,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             const float bot = __fmul_rn(__fadd_rn(p10, p11), ya);
             const float res = __fadd_rn(top, bot);
             // round-half-even via the 1.5*2^23 trick; res <= 255*(1 + 1e-6), so the result is already in [0,255]
-            // RAW: the bias 0x6400 rides along in the magic constant and the float's upper bits are left in place; only the
+            // RAW: the float's upper bits are left in place (with RV_PLANE_BIASED the bias 0x6400 also rides along in the magic constant); only the
             // low 16 bits of the sums below are ever used (pack2 keeps the low halves), so no masking is needed.
             // YCrCb: - 256 because the tables' f fields and the G sum carry + 256.
             constexpr float MAGIC = 12582912.0f + ((RAW && RV_PLANE_BIASED) ? 25600.0f : 0.0f) - (MODE == 0 ? 256.0f : 0.0f);
@@ -479,7 +479,7 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             }
         }
     };
-    // two rows' values of one pixel/channel -> one plane word (low half = first row), saturated and biased
+    // two rows' values of one pixel/channel -> one plane word (low half = first row), saturated
     auto pack2 = [&](int lo, int hi) -> uint32_t {
         const uint32_t w = __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
 #if RV_PLANE_BIASED
