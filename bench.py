@@ -343,8 +343,17 @@ def load_ncu_constants(rvb200):
         j = json.load(open(path))
     except Exception:
         return None, {"traffic_source": None, "tree_hash": tree, "note": "profiles/final_k_chain.json missing"}
-    info = {"traffic_source": "profiles/final_k_chain.json", "capture_hash": j.get("source_hash"), "tree_hash": tree,
-            "hash_match": j.get("source_hash") == tree, "capture": j.get("capture")}
+    # the capture is tied to the BINARY: the SASS of the measured kernel in the library loaded here must be the SASS the capture ran
+    # on (a change elsewhere in csrc/ -- another instantiation's network, host code -- leaves it valid); the hash over the kernel
+    # sources is reported next to it
+    try:
+        built = rvb200.kernel_sass_hash(j["kernel"])
+    except Exception as e:                                   # cuobjdump missing: fall back to the source hash alone
+        built = "unavailable: %s" % (str(e)[:80],)
+    info = {"traffic_source": "profiles/final_k_chain.json", "capture": j.get("capture"), "kernel": j.get("kernel", "").split("(")[0],
+            "capture_sass_hash": j.get("sass_hash"), "built_sass_hash": built,
+            "capture_hash": j.get("source_hash"), "tree_hash": tree,
+            "hash_match": (j.get("sass_hash") is not None and j.get("sass_hash") == built) or j.get("source_hash") == tree}
     return j, info
 
 

@@ -1,6 +1,7 @@
 """ctypes binding of librv_b200.so (include/rv_b200.h).  Plumbing only -- no arithmetic here."""
 import ctypes as C
 import os
+import shutil
 import subprocess
 import threading
 import weakref
@@ -103,6 +104,46 @@ def kernel_source_hash():
         text = " ".join(text.split())
         h.update(name.encode() + b"\0" + text.encode() + b"\0")
     return h.hexdigest()[:16]
+
+
+_sass_cache = {}
+
+
+def kernel_sass_hashes(so=None):
+    """{demangled kernel name: SHA-256 (first 16 hex digits) of its SASS listing} for every kernel in the built library
+    (`cuobjdump -sass`, names through `cu++filt`).  This is the tie between a profile and the BINARY: an ncu capture stays valid
+    for as long as the machine code of the kernel it measured is unchanged, whatever else is edited in csrc/ (another
+    instantiation's network, a comment, host code); profiles/final_*.json record it as `sass_hash` next to `source_hash`."""
+    import hashlib
+    import re
+    so = so or _SO
+    key = (so, os.path.getmtime(so))
+    if key in _sass_cache:
+        return _sass_cache[key]
+    cuda_bin = os.path.dirname(shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump")
+    text = subprocess.run([os.path.join(cuda_bin, "cuobjdump"), "-sass", so], capture_output=True, text=True, check=True).stdout
+    parts = re.split(r"^\s*Function : (\S+)\s*$", text, flags=re.M)
+    names, bodies = parts[1::2], parts[2::2]
+    dem = subprocess.run([os.path.join(cuda_bin, "cu++filt")] + names, capture_output=True, text=True, check=True).stdout.splitlines()
+    out = {}
+    for n, body in zip(dem, bodies):
+        body = body.split("Fatbin elf code:")[0]
+        body = "\n".join(ln.strip() for ln in body.splitlines() if ln.strip() and not ln.strip().startswith(("=", ".")))
+        n = re.sub(r"\((?:int|bool)\)", "", n).replace("rv::", "")
+        out[n] = hashlib.sha256(body.encode()).hexdigest()[:16]
+    _sass_cache[key] = out
+    return out
+
+
+def kernel_sass_hash(kernel, so=None):
+    """SASS hash of one kernel, named the way ncu prints it (e.g. 'k_chain<0, 5>'; a prefix of the full signature is enough)."""
+    import re
+    want = re.sub(r"^void\s+", "", kernel).replace("rv::", "")
+    want = want.split("(")[0].replace(" ", "")
+    hits = [h for n, h in kernel_sass_hashes(so).items() if re.sub(r"^void\s+", "", n).split("(")[0].replace(" ", "") == want]
+    if len(hits) != 1:
+        raise KeyError(f"kernel {kernel!r} not found (or ambiguous) in {so or _SO}")
+    return hits[0]
 
 
 _lib = None

@@ -32,6 +32,14 @@
 #ifndef RV_MEDIAN3_2ROW
 #define RV_MEDIAN3_2ROW 1
 #endif
+// k = 7, 9: the same two-row scheme from the generic hierarchical builder (tools/gen_median_net.py: build_hier_2rows): 143 / 290
+// packed operations per output instead of 222 / 605 -> 1080p k7 26.1 k -> 37.2 k fps, k9 11.1 k -> 19.8 k (profiles/r2_y_median79_two_rows.txt)
+#ifndef RV_MEDIAN7_2ROW
+#define RV_MEDIAN7_2ROW 1
+#endif
+#ifndef RV_MEDIAN9_2ROW
+#define RV_MEDIAN9_2ROW 1
+#endif
 __device__ __forceinline__ void rv_ce_fma(uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi)
 {
     const __half2 x = *reinterpret_cast<const __half2 *>(&a), y = *reinterpret_cast<const __half2 *>(&b);
@@ -161,8 +169,11 @@ struct ChainSmem {
 #ifndef RV_CHAIN_MIN_CTAS
 #define RV_CHAIN_MIN_CTAS 2
 #endif
+#ifndef RV_CHAIN_MIN_CTAS_BIG
+#define RV_CHAIN_MIN_CTAS_BIG 2        // k = 7, 9: a 128-register cap keeps two CTAs per SM (the k9 network spills ~36 bytes; one CTA per SM
+#endif                                 // with 153 registers and no spill is 15 % slower)
 template <int MODE, int K>
-__global__ void __launch_bounds__(CHAIN_THREADS, (K <= 5 ? RV_CHAIN_MIN_CTAS : 1))
+__global__ void __launch_bounds__(CHAIN_THREADS, (K <= 5 ? RV_CHAIN_MIN_CTAS : RV_CHAIN_MIN_CTAS_BIG))
 k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
 {
     using S = ChainSmem<MODE, K>;
@@ -541,10 +552,10 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
     __syncthreads();
 
     // ---- phase 2: k x k median per channel plane; lanes of each u16x2 are output rows (s, s+HALF)
-    constexpr bool TWO_ROW = (K == 5 && RV_MEDIAN5_2ROW) || (K == 3 && RV_MEDIAN3_2ROW);
+    constexpr bool TWO_ROW = (K == 5 && RV_MEDIAN5_2ROW) || (K == 3 && RV_MEDIAN3_2ROW) || (K == 7 && RV_MEDIAN7_2ROW) || (K == 9 && RV_MEDIAN9_2ROW);
     if constexpr (TWO_ROW) {
         // two vertically adjacent output rows per task (slots s, s+1): the K-1 middle window rows are shared
-        constexpr int M = (K == 5) ? RV_MEDIAN5X2_M : RV_MEDIAN3X2_M;
+        constexpr int M = (K == 5) ? RV_MEDIAN5X2_M : (K == 3) ? RV_MEDIAN3X2_M : (K == 7) ? RV_MEDIAN7X2_M : RV_MEDIAN9X2_M;
         constexpr int NG = TILE_W / M;
         constexpr int NC = M + K - 1;
         constexpr int NR = K + 1;                    // plane rows per task
@@ -601,6 +612,8 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
             }
             uint32_t out[2][M];
             if constexpr (K == 5) rv_median5x2_net(v, out);
+            else if constexpr (K == 7) rv_median7x2_net(v, out);
+            else if constexpr (K == 9) rv_median9x2_net(v, out);
             else rv_median3x2_net(v, out);
 #pragma unroll
             for (int hrow = 0; hrow < 2; ++hrow) {
@@ -640,16 +653,22 @@ k_chain(const ChainArgs a, const __grid_constant__ CUtensorMap tmap)
 #pragma unroll
                     for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[C0 + cc];
                 }
-            } else if constexpr (C0 % 2 == 0 && M % 2 == 0 && NC % 2 == 0) {
-                // 8-byte loads; with M = 6 the 16 lanes of a phase hit 16 distinct even banks (6m+2 mod 32)
+            } else if constexpr (M % 2 == 0) {
+                // 8-byte loads from the even word at or below the first needed column; with M = 6 the 16 lanes of a phase hit 16
+                // distinct even banks (6m+2 mod 32)
+                constexpr int C0E = C0 & ~1, SKIP = C0 - C0E, NW = (SKIP + NC + 1) / 2;
+                static_assert(TILE_W - M + C0E + 2 * NW <= P_STRIDE, "median loads stay inside the plane row");
 #pragma unroll
                 for (int d = 0; d < K; ++d) {
-                    const uint2 *p2 = reinterpret_cast<const uint2 *>(pc + d * P_STRIDE + M * m + C0);
+                    const uint2 *p2 = reinterpret_cast<const uint2 *>(pc + d * P_STRIDE + M * m + C0E);
+                    uint32_t w[2 * NW];
 #pragma unroll
-                    for (int cc = 0; cc < NC / 2; ++cc) {
+                    for (int cc = 0; cc < NW; ++cc) {
                         const uint2 q = p2[cc];
-                        v[2 * cc][d] = q.x; v[2 * cc + 1][d] = q.y;
+                        w[2 * cc] = q.x; w[2 * cc + 1] = q.y;
                     }
+#pragma unroll
+                    for (int cc = 0; cc < NC; ++cc) v[cc][d] = w[SKIP + cc];
                 }
             } else {
 #pragma unroll

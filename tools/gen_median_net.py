@@ -30,8 +30,11 @@ SORTERS = {
     3: [(0, 2), (0, 1), (1, 2)],
     4: [(0, 2), (1, 3), (0, 1), (2, 3), (1, 2)],
     5: [(0, 3), (1, 4), (0, 2), (1, 3), (0, 1), (2, 4), (1, 2), (3, 4), (2, 3)],
+    6: [(0, 5), (1, 3), (2, 4), (1, 2), (3, 4), (0, 3), (2, 5), (0, 1), (2, 3), (4, 5), (1, 2), (3, 4)],
     7: [(0, 6), (2, 3), (4, 5), (0, 2), (1, 4), (3, 6), (0, 1), (2, 5), (3, 4), (1, 2), (4, 6),
         (2, 3), (4, 5), (1, 2), (3, 4), (5, 6)],
+    8: [(0, 2), (1, 3), (4, 6), (5, 7), (0, 4), (1, 5), (2, 6), (3, 7), (0, 1), (2, 3), (4, 5), (6, 7), (2, 4), (3, 5),
+        (1, 4), (3, 6), (1, 2), (3, 4), (5, 6)],
     9: [(0, 3), (1, 7), (2, 5), (4, 8), (0, 7), (2, 4), (3, 8), (5, 6), (0, 2), (1, 3), (4, 5), (7, 8),
         (1, 4), (3, 6), (5, 7), (0, 1), (2, 4), (3, 5), (6, 8), (2, 3), (4, 5), (6, 7), (1, 2), (3, 4), (5, 6)],
 }
@@ -366,6 +369,68 @@ def build3_2rows(M, parity):
     return d, inp, outs
 
 
+def build_hier_2rows(k, M, parity, rparity=0):
+    """Any odd k >= 5, two vertically adjacent output rows per call (window rows 0..k-1 and 1..k of k+1 input rows): the k-1
+    middle rows are shared.  Their columns are sorted once, merged in pairs P(a) (a of the given parity) and, pair after pair,
+    into H(a) -- after every merge only the ranks that can still hold the median of k*k are kept -- and joined with the
+    remaining column: core(o) = the k+1 candidates among the k(k-1) shared elements of window o.  Each output then takes one
+    rank of core(o) u its own sorted outer row window; the row windows of two horizontal neighbours share the sorted k-1
+    elements they have in common (aligned ordered pairs merged, the pairs shared between groups) and insert one element each."""
+    d = Dag()
+    ncol = M + k - 1
+    half = (k * k) // 2
+    inp = [[d.inp((c, r)) for r in range(k + 1)] for c in range(ncol)]
+    colc = [d.sort([inp[c][r] for r in range(1, k)]) for c in range(ncol)]
+    P, H, core, rowwin = {}, {}, {}, {}
+
+    def pair(a):
+        if a not in P:
+            P[a] = d.merge(colc[a], colc[a + 1])
+        return P[a]
+
+    def trim(lst, below, rest):
+        t = half - below
+        lo, hi = max(0, t - rest), min(len(lst) - 1, t)
+        return lst[lo:hi + 1], below + lo
+
+    def hexa(a):
+        if a not in H:
+            npairs = (k - 1) // 2
+            acc, below, used = pair(a), 0, 2
+            for i in range(1, npairs):
+                used += 2
+                acc, below = trim(d.merge(acc, pair(a + 2 * i)), below, (k - used) * (k - 1) + k)
+            H[a] = (acc, below)
+        return H[a]
+
+    def core_of(o):
+        if o not in core:
+            (acc, below), single = (hexa(o), colc[o + k - 1]) if o % 2 == parity else (hexa(o + 1), colc[o])
+            core[o] = trim(d.merge(acc, single), below, k)
+        return core[o]
+
+    def rw(r, o):
+        if (r, o) not in rowwin:
+            b = o if o % 2 == rparity else o - 1
+            if b >= 0 and b + k < ncol:
+                e = [inp[c][r] for c in range(b + 1, b + k)]            # the k-1 elements windows b and b+1 share
+                acc = d.sort(e[:2])
+                for i in range(2, k - 1, 2):
+                    acc = d.merge(acc, d.sort(e[i:i + 2]))
+                rowwin[(r, b)] = d.merge([inp[b][r]], acc)
+                rowwin[(r, b + 1)] = d.merge([inp[b + k][r]], acc)
+            else:
+                rowwin[(r, o)] = d.sort([inp[c][r] for c in range(o, o + k)])
+        return rowwin[(r, o)]
+
+    outs = []
+    for r in (0, k):
+        for o in range(M):
+            acc, below = core_of(o)
+            outs.append(d.kth2(acc, rw(r, o), half - below + 1))
+    return d, inp, outs
+
+
 def verify_2rows_generic(d, inp, outs, k, M, zero_one=True, trials=20000):
     rng = np.random.RandomState(2)
     ncol = M + k - 1
@@ -382,6 +447,27 @@ def verify_2rows_generic(d, inp, outs, k, M, zero_one=True, trials=20000):
         for half in range(2):
             sub = [[inp[c][half + r] for r in range(k)] for c in range(ncol)]
             if not verify_zero_one(d, sub, outs[half * M:(half + 1) * M], k, M):
+                return False
+    return True
+
+
+def verify_threshold_random(d, inp_windows, outs, k, trials=60000, seed=5):
+    """0-1 vectors at the threshold, for the networks that are too wide for the exhaustive 0-1 check (k = 7, 9).  A min/max
+    network computes a monotone Boolean function; it is the median iff that function is 'at least (k*k+1)/2 ones', so the inputs
+    that can expose a wrong network are the ones with exactly (k*k-1)/2 ones inside a window (must give 0) and exactly
+    (k*k+1)/2 (must give 1).  inp_windows[o] = the k*k input nodes of output o; the other inputs are random bits."""
+    rng = np.random.RandomState(seed)
+    all_inputs = sorted({n for n in d.live(outs) if d.nodes[n][0] == "in"})
+    kk = k * k
+    for o, (win, out) in enumerate(zip(inp_windows, outs)):
+        for ones in (kk // 2, kk // 2 + 1):
+            vals = {n: rng.randint(0, 2, trials).astype(np.uint8) for n in all_inputs}
+            order = np.argsort(rng.rand(trials, kk), axis=1)                 # a random subset of `ones` positions per trial
+            bits = (order < ones).astype(np.uint8)
+            for j, n in enumerate(win):
+                vals[n] = bits[:, j]
+            got = evaluate(d, None, [out], vals)[0]
+            if not np.all(got == (1 if ones > kk // 2 else 0)):
                 return False
     return True
 
@@ -566,14 +652,15 @@ def emit(d, inputs, outs, k, M, fh):
     return nops
 
 
-CONFIG = {3: 4, 5: int(os.environ.get('RV_MEDIAN5_M', '6')), 7: int(os.environ.get('RV_MEDIAN7_M', '4')), 9: 2}     # k -> outputs per call
+CONFIG = {3: 4, 5: int(os.environ.get('RV_MEDIAN5_M', '6')), 7: int(os.environ.get('RV_MEDIAN7_M', '4')),
+          9: int(os.environ.get('RV_MEDIAN9_M', '2'))}     # k -> outputs per call
 
 
 def main():
     for n, net in SORTERS.items():
         assert check_sorter(n, net), f"sorter {n} is wrong"
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    path = os.path.join(root, "road-vision-system_b200", "csrc", "rv_median_net.h")
+    path = os.environ.get("RV_MEDIAN_NET_OUT") or os.path.join(root, "road-vision-system_b200", "csrc", "rv_median_net.h")
     quick = "--quick" in sys.argv
     with open(path, "w") as fh:
         fh.write("/* GENERATED by tools/gen_median_net.py -- do not edit.\n"
@@ -586,7 +673,8 @@ def main():
                  "/* per-network compare-exchange macros (the kernel may give each network its own ALU/FMA mix) */\n"
                  "#ifndef RV_CEX3\n#define RV_CEX3 RV_CEX\n#endif\n#ifndef RV_CEX5\n#define RV_CEX5 RV_CEX\n#endif\n"
                  "#ifndef RV_CEX7\n#define RV_CEX7 RV_CEX\n#endif\n#ifndef RV_CEX9\n#define RV_CEX9 RV_CEX\n#endif\n"
-                 "#ifndef RV_CEX5X2\n#define RV_CEX5X2 RV_CEX\n#endif\n#ifndef RV_CEX3X2\n#define RV_CEX3X2 RV_CEX\n#endif\n\n")
+                 "#ifndef RV_CEX5X2\n#define RV_CEX5X2 RV_CEX\n#endif\n#ifndef RV_CEX3X2\n#define RV_CEX3X2 RV_CEX\n#endif\n"
+                 "#ifndef RV_CEX7X2\n#define RV_CEX7X2 RV_CEX\n#endif\n#ifndef RV_CEX9X2\n#define RV_CEX9X2 RV_CEX\n#endif\n\n")
         for k, M in CONFIG.items():
             best = None
             for strat, parity in (("pairs", 0), ("pairs", 1), ("flat", 0), ("quads", 0), ("quads", 1), ("hier", 0), ("hier", 1)):
@@ -604,6 +692,9 @@ def main():
                     best = (nops, f"{strat}/parity{parity}", d, inputs, outs)
             nops, strat, d, inputs, outs = best
             assert verify_random(d, inputs, outs, k, M), f"k={k}: random verification failed"
+            if k > 5:
+                wins = [[inputs[c][r] for c in range(o, o + k) for r in range(k)] for o in range(M)]
+                assert verify_threshold_random(d, wins, outs, k, trials=20000 if quick else 60000), f"k={k}: threshold 0-1 vectors failed"
             if not quick:
                 z = verify_zero_one(d, inputs, outs, k, M)
                 assert z in (True, None), f"k={k}: 0-1 verification failed"
@@ -634,6 +725,21 @@ def main():
         assert verify_2rows_generic(d, inp, outs, 3, M3, zero_one=not quick), "k=3 two-row network failed verification"
         emit_2rows(d, inp, outs, M3, fh, k=3)
         print(f"k=3 two rows M={M3} parity={parity}: {nops} ops ({nops / (2 * M3):.1f}/output), zero-one={'skipped' if quick else True}")
+        for k in (7, 9):
+            Mk = int(os.environ.get(f"RV_MEDIAN{k}X2_M", {7: "6", 9: "4"}[k]))       # measured: profiles/r2_y_median79_two_rows.txt
+            best = None
+            for parity in (0, 1):
+                for rpar in (0, 1):
+                    d, inp, outs = build_hier_2rows(k, Mk, parity, rpar)
+                    nops = sum(1 for n in d.live(outs) if d.nodes[n][0] != "in")
+                    if best is None or nops < best[0]:
+                        best = (nops, parity, rpar, d, inp, outs)
+            nops, parity, rpar, d, inp, outs = best
+            assert verify_2rows_generic(d, inp, outs, k, Mk, zero_one=False), f"k={k} two-row network failed verification"
+            wins = [[inp[c][hrow + r] for c in range(o, o + k) for r in range(k)] for hrow in (0, 1) for o in range(Mk)]
+            assert verify_threshold_random(d, wins, outs, k, trials=20000 if quick else 60000), f"k={k} two rows: threshold 0-1 vectors failed"
+            emit_2rows(d, inp, outs, Mk, fh, k=k)
+            print(f"k={k} two rows M={Mk} parity={parity}/{rpar}: {nops} ops ({nops / (2 * Mk):.1f}/output), random vectors + 0-1 vectors at the threshold")
         fh.write("#endif\n")
     print("wrote", path)
 

@@ -3,8 +3,9 @@
 usage: tools/ncu_summary.py gpurun_out/prof_chain_TAG.ncu-rep [out.txt] [--json profiles/final_k_chain.json]
 
 --json also writes the per-launch constants bench.py reports (DRAM bytes, executed warp instructions, duration) together with
-the hash of the kernel sources they were measured on (rvb200.kernel_source_hash()); bench.py and tests/test_host_logic.py
-refuse constants whose hash differs from the tree."""
+the hash of the kernel sources they were measured on (rvb200.kernel_source_hash()) and the hash of the measured kernel's SASS
+(rvb200.kernel_sass_hash()); bench.py and tests/test_host_logic.py refuse constants when neither the sources nor the kernel's
+machine code in the built library are the ones the capture ran on."""
 import collections
 import csv
 import io
@@ -45,7 +46,15 @@ def write_json(path, rep, hdr, d):
     def to_us(name):
         u = unit[name].lower()
         return num(name) * {'ns': 1e-3, 'us': 1, 'usecond': 1, 'nsecond': 1e-3, 'ms': 1e3, 'msecond': 1e3}[u]
-    j = {"kernel": d[hdr.index('Kernel Name')], "capture": os.path.basename(rep), "source_hash": HASH[0] if HASH else rvb200.kernel_source_hash(),
+    kname = d[hdr.index('Kernel Name')]
+    if SASS:                                        # per-kernel SASS hashes recorded on the GPU box when the capture was taken
+        import re
+        norm = lambda n: re.sub(r"^void\s+", "", n).split("(")[0].replace(" ", "")
+        sass = {norm(k): v for k, v in json.load(open(SASS[0])).items()}[norm(kname)]
+    else:
+        sass = rvb200.kernel_sass_hash(kname)
+    j = {"kernel": kname, "capture": os.path.basename(rep), "source_hash": HASH[0] if HASH else rvb200.kernel_source_hash(),
+         "sass_hash": sass,
          "grid": d[hdr.index('Grid Size')] if 'Grid Size' in hdr else None,
          "dram_bytes_read": to_bytes('dram__bytes_read.sum'), "dram_bytes_write": to_bytes('dram__bytes_write.sum'),
          "warp_instructions": num('smsp__inst_executed.sum'), "duration_us_under_ncu": to_us('gpu__time_duration.sum'),
@@ -62,6 +71,7 @@ def write_json(path, rep, hdr, d):
 
 UNITS = []
 HASH = []
+SASS = []
 
 
 def main():
@@ -70,6 +80,10 @@ def main():
     if '--hash-file' in args:                       # hash recorded on the GPU box when the capture was taken
         i = args.index('--hash-file')
         HASH[:] = [open(args[i + 1]).read().strip()]
+        del args[i:i + 2]
+    if '--sass-file' in args:                       # {kernel: SASS hash} of the library the capture ran on (rvb200.kernel_sass_hashes())
+        i = args.index('--sass-file')
+        SASS[:] = [args[i + 1]]
         del args[i:i + 2]
     if '--json' in args:
         i = args.index('--json')
