@@ -63,6 +63,13 @@ __device__ __forceinline__ void rv_ce_fma(uint32_t a, uint32_t b, uint32_t &lo, 
 #endif
 #define RV_CEX3(n, lo, hi, a, b) RV_CEX_MIX(RV_FMA3_NUM, RV_FMA3_DEN, n, lo, hi, a, b)
 #define RV_CEX3X2 RV_CEX3              // the production 3x3 network (two rows per task) takes the k3 mix
+// the 7x7 / 9x9 two-row networks (their kernels are almost nothing but the median)
+#ifndef RV_FMA79_NUM
+#define RV_FMA79_NUM RV_FMA_NUM
+#define RV_FMA79_DEN RV_FMA_DEN
+#endif
+#define RV_CEX7X2(n, lo, hi, a, b) RV_CEX_MIX(RV_FMA79_NUM, RV_FMA79_DEN, n, lo, hi, a, b)
+#define RV_CEX9X2(n, lo, hi, a, b) RV_CEX_MIX(RV_FMA79_NUM, RV_FMA79_DEN, n, lo, hi, a, b)
 
 #ifndef RV_MEDIAN_NET_FILE
 #define RV_MEDIAN_NET_FILE "rv_median_net.h"      // tools/exp_median_order.py builds the kernel against alternative emissions
