@@ -63,10 +63,12 @@ __device__ __forceinline__ void rv_ce_fma(uint32_t a, uint32_t b, uint32_t &lo, 
 #endif
 #define RV_CEX3(n, lo, hi, a, b) RV_CEX_MIX(RV_FMA3_NUM, RV_FMA3_DEN, n, lo, hi, a, b)
 #define RV_CEX3X2 RV_CEX3              // the production 3x3 network (two rows per task) takes the k3 mix
-// the 7x7 / 9x9 two-row networks (their kernels are almost nothing but the median)
+// the 7x7 / 9x9 two-row networks: their kernels are almost nothing but the median, and 3/7 of the compare-exchanges on the FMA pipe is
+// close to where the ALU-pipe, FMA-pipe and issue limits of a pure compare-exchange stream meet (f = 0.4).  Measured against 1/2:
+// k7 +1.6 %, k9 +3.5 % (1/3: -2.5 % / +3.4 %, 2/5: +1.0 % / +3.1 %, 3/5: -5 % / -9 %; profiles/r2_aa_median79_mix.txt)
 #ifndef RV_FMA79_NUM
-#define RV_FMA79_NUM RV_FMA_NUM
-#define RV_FMA79_DEN RV_FMA_DEN
+#define RV_FMA79_NUM 3
+#define RV_FMA79_DEN 7
 #endif
 #define RV_CEX7X2(n, lo, hi, a, b) RV_CEX_MIX(RV_FMA79_NUM, RV_FMA79_DEN, n, lo, hi, a, b)
 #define RV_CEX9X2(n, lo, hi, a, b) RV_CEX_MIX(RV_FMA79_NUM, RV_FMA79_DEN, n, lo, hi, a, b)

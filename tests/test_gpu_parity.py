@@ -64,6 +64,19 @@ def test_median_alone(ctx, k):
     assert np.array_equal(ctx.median(ties[None], k)[0], O.median(ties, k))
 
 
+@pytest.mark.parametrize("k", [3, 5, 7, 9])
+def test_median_zero_one_frames(ctx, k):
+    """0-1 principle on the device code itself: a min/max selection network is the median iff it is right on 0-1 inputs, and the
+    inputs that can tell a wrong network apart have about half ones in the window.  Random binary frames (two grey levels) with
+    densities around 1/2 put hundreds of thousands of windows per channel at exactly (k*k-1)/2 and (k*k+1)/2 ones; the frame is
+    wider than one 120-pixel tile and taller than one 48-row tile, so every group, lane (rows s / s+24) and tile edge is hit."""
+    h, w = 200, 380
+    for dens, lo, hi, seed in [(0.5, 0, 255, 1), (0.47, 17, 18, 2), (0.53, 254, 255, 3), (0.5, 0, 1, 4)]:
+        rng = np.random.RandomState(100 * k + seed)
+        img = np.where(rng.rand(h, w, 3) < dens, hi, lo).astype(np.uint8)
+        assert np.array_equal(ctx.median(img[None], k)[0], O.median(img, k)), (k, dens, lo, hi)
+
+
 @pytest.mark.parametrize("space", ["YCrCb", "LAB"])
 def test_clahe_dehaze_alone(ctx, space):
     for name, img in frames_small():
