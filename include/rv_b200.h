@@ -86,6 +86,7 @@ const char *rv_last_error(const rv_ctx *ctx);
 
 /* tuning knobs: "group_frames" (frames per hist->lut->apply pass, sized for L2 residency),
  * "chunk_frames" (frames per H2D/compute/D2H pipeline stage for host memory), 0 = automatic;
+ * "chunk_taper" (default 1: a host job starts and ends with smaller chunks so that the pipeline fills and drains faster; 0 = uniform);
  * "kernel_timing" (0/1, see rv_kernel_time); "use_tma" (default 1; 0 forces the plain-load staging path);
  * "prefetch_ctas" (default 0 = off: k_chain also prefetches into L2 the box of the CTA that many resident-CTA generations
  * ahead; measured 0.8 % slower on B200, the staging wait is already hidden by the co-resident CTAs);
