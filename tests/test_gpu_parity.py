@@ -200,6 +200,34 @@ def test_batch_equals_per_frame_and_pinned(ctx):
         ctx.set_option("group_frames", 0)
 
 
+def test_host_pipeline_chunk_schedules(ctx):
+    """Every chunk schedule of the host pipeline (uniform / tapered ends, chunk sizes 2..6, batch sizes around the multiples of the
+    chunk size) returns the frames of the per-frame path, each exactly once and in order; the detector tensor likewise."""
+    import rvb200
+    from rvb200 import synth
+    pool = synth.frame_pool(96, 168, 6, base_seed=77)
+    cfg = {"chain": [{"name": "CLAHEDehaze", "params": {"space": "LAB", "tile_grid": 4}}, {"name": "MedianDerain", "params": {"ksize": 3}}]}
+    pl = rvb200.PreprocessPipeline(cfg)
+    per_frame = [pl(f) for f in pool]
+    try:
+        for taper in (1, 0):
+            ctx.set_option("chunk_taper", taper)
+            for chunk in (2, 3, 4, 6):
+                ctx.set_option("chunk_frames", chunk)
+                for n in (1, 2, 3 * chunk, 3 * chunk + 1, 4 * chunk - 1, 5 * chunk + 2, 23):
+                    idx = [(5 * i + n) % len(pool) for i in range(n)]
+                    frames = np.stack([pool[i] for i in idx])
+                    got = pl.process_batch(frames)
+                    assert all(np.array_equal(got[j], per_frame[i]) for j, i in enumerate(idx)), (taper, chunk, n)
+                    if chunk == 3:
+                        t, _ = pl.process_batch_to_tensor(frames, size=64)
+                        want, _ = pl.process_batch_to_tensor(frames[:1], size=64)
+                        assert np.array_equal(t[0].view(np.uint16), want[0].view(np.uint16)) and t.shape == (n, 3, 64, 64), (taper, n)
+    finally:
+        ctx.set_option("chunk_frames", 0)
+        ctx.set_option("chunk_taper", 1)
+
+
 def test_batch_gate_passthrough(ctx):
     import rvb200
     rng = np.random.RandomState(9)
