@@ -678,6 +678,37 @@ def test_contexts_are_independent_across_threads():
     assert not errors, errors
 
 
+def test_context_lifecycle_returns_its_memory():
+    """Contexts come and go with camera streams: creating one, running frames of several geometries through every kind of entry
+    (per-frame with graphs, host batch, device-resident results, detector tensor) and closing it gives all device memory back."""
+    import torch
+    import rvb200
+    from rvb200 import synth
+    cfg = {"chain": [{"name": "CLAHEDehaze", "params": {"space": "YCrCb"}}, {"name": "MedianDerain", "params": {"ksize": 5}}]}
+    shapes = [(270, 480), (360, 640), (135, 300)]
+    pools = [synth.frame_pool(h, w, 5, base_seed=900 + i) for i, (h, w) in enumerate(shapes)]
+
+    def cycle():
+        c = rvb200.Context(0)
+        pl = rvb200.PreprocessPipeline(cfg, context=c)
+        for fr in pools:
+            pl(fr[0]); pl(fr[1])
+            pl.process_batch(fr)
+            pin = c.pinned_empty(fr.shape); pin[:] = fr
+            dev, _ = pl.process_batch_to_tensor(pin, size=96, out="device")
+            del dev, pin
+        c.close()
+
+    cycle()                                        # first cycle: one-time allocations of the CUDA runtime and the module's tables
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info(0)[0]
+    for _ in range(8):
+        cycle()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info(0)[0]
+    assert free0 - free1 < (8 << 20), f"{(free0 - free1) >> 20} MiB of device memory not returned after 8 context life cycles"
+
+
 def test_tensor_rows_only_download(ctx):
     """padding_present: a host tensor buffer that already holds the letterbox padding rows gets only its image rows back over PCIe;
     the complete tensor equals the ordinary one (fused 1080p, unfused ragged, and a portrait frame whose padding is left / right)."""
