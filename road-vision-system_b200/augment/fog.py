@@ -40,6 +40,41 @@ class FogFrame(C.Structure):
     ]
 
 
+_FAST_QUANTILE = None
+
+
+def _quantile09_fast(flat):
+    """np.quantile(flat, 0.9) for a 1-D float32 array from one np.partition: numpy's linear method interpolates between the order
+    statistics k and k + 1 at the fractional part of the virtual index (n - 1) q, evaluated in the array's own precision; the
+    interpolation itself is left to numpy (np.quantile of the two values at that fractional position)."""
+    vi = (flat.size - 1) * np.asarray(0.9, dtype=flat.dtype)
+    lo = np.floor(vi)
+    k = int(lo)
+    if k + 1 >= flat.size:
+        return np.quantile(flat, 0.9)
+    part = np.partition(flat, k)                                      # part[k] = order statistic k, everything right of it is >= it
+    pair = np.array([part[k], part[k + 1:].min()], dtype=flat.dtype)
+    return np.quantile(pair, float(vi - lo))
+
+
+def _quantile09(flat):
+    """The fast form where it reproduces this numpy's np.quantile bit for bit (checked once per process on arrays with distinct
+    values, ties and neighbouring floats), np.quantile itself otherwise -- the threshold must be the reference's."""
+    global _FAST_QUANTILE
+    if _FAST_QUANTILE is None:
+        rng, ok = np.random.RandomState(12345), flat.dtype == np.float32
+        for n in (12, 101, 1000, 1877, 4096, 24769):
+            for x in (rng.rand(n), rng.randint(0, 5, n) / 7.0, 0.5 + np.arange(n) * 6e-8, rng.normal(0.7, 1e-6, n)):
+                x = x.astype(np.float32)
+                rng.shuffle(x)
+                a, b = _quantile09_fast(x), np.quantile(x, 0.9)
+                ok = ok and a.dtype == b.dtype and a == b
+        _FAST_QUANTILE = bool(ok)
+    if _FAST_QUANTILE and flat.dtype == np.float32:
+        return _quantile09_fast(flat)
+    return np.quantile(flat, 0.9)
+
+
 def _logistic(z):
     return 1.0 / (1.0 + np.exp(-z))
 
@@ -124,14 +159,52 @@ class EnhancedFogSynthesizer:
         return shapes, np.concatenate(chunks)
 
     def _airlight_colour(self, bgr):
-        """Mean colour of the brightest tenth of the top 12 % of the frame, tinted and clipped (fog.py:120-131)."""
+        """Mean colour of the brightest tenth of the top 12 % of the frame, tinted and clipped (fog.py:120-131).  The same float32
+        values as the reference's `lum >= np.quantile(lum, 0.9)` / `top[mask].mean(axis=0)`, obtained with less work: the two order
+        statistics the 0.9-quantile interpolates between come from one `np.partition`, the interpolation itself is numpy's own
+        (`np.quantile` of those two values at the same fractional position), and the selected pixels are gathered by index."""
         h = bgr.shape[0]
         top = bgr[:max(10, int(0.12 * h))].astype(np.float32) / 255.0
         lum = 0.299 * top[:, :, 2] + 0.587 * top[:, :, 1] + 0.114 * top[:, :, 0]
-        bright = lum >= np.quantile(lum, 0.9)
-        colour = (top[bright].mean(axis=0) if bright.sum() >= 100 else top.mean(axis=(0, 1))).astype(np.float32)
+        flat = lum.ravel()
+        thr = _quantile09(flat)
+        sel = np.flatnonzero(flat >= thr)
+        colour = (top.reshape(-1, 3)[sel].mean(axis=0) if sel.size >= 100 else top.mean(axis=(0, 1))).astype(np.float32)
         tint = self.rng.uniform(-0.02, 0.02, size=3).astype(np.float32)
         return np.clip(colour + tint, 0.7, 1.0)
+
+    def _band_radii(self, geo, base_beta):
+        """Gaussian sizes of the three depth-blur bands: int(max(1, 1.5 * mean(r in band))) | 1 with r = clip(depth * depth_blur_max *
+        (0.5 + beta), 0, 1.5 depth_blur_max) (fog.py:203-213).  The mean over a band is a float32 reduction over up to 2 M pixels per
+        frame in the reference; here depth * depth_blur_max and its float64 mean are kept per geometry, and the per-frame value
+        s * mean decides the integer whenever it is not within 1e-4 of an integer boundary (and nothing is clipped) -- otherwise the
+        reference's own reduction is evaluated, so the result is always the reference's integer."""
+        dmax = float(self.depth_blur_max)
+        cache = geo.setdefault("band_cache", {})
+        if dmax not in cache:
+            ent = []
+            for count, vals in geo["bands"]:
+                if count >= 100:
+                    x = vals * dmax
+                    ent.append((count, x, float(x.astype(np.float64).mean()), float(x.max()), float(x.min())))
+                else:
+                    ent.append((count, None, 0.0, 0.0, 0.0))
+            cache[dmax] = ent
+        s = 0.5 + base_beta
+        s32 = float(np.float32(s))
+        out = []
+        for count, x, m64, xmax, xmin in cache[dmax]:
+            rad = 0
+            if count >= 100:
+                est = s32 * m64 * 1.5
+                safe = xmin >= 0.0 and s32 >= 0.0 and xmax * s32 * (1 + 1e-6) < dmax * 1.5 and abs(est - round(est)) > 1e-4 * max(1.0, est)
+                if safe:
+                    rad = int(max(1, est)) | 1
+                else:
+                    r = np.clip(x * s, 0.0, dmax * 1.5)
+                    rad = int(max(1, np.mean(r) * 1.5)) | 1
+            out.append(rad if rad > 1 else 0)
+        return out
 
     def synthesize(self, bgr_uint8, level=None, meta=True):
         """BGR uint8 frame -> (hazy BGR uint8 frame, meta with beta_map / A_map / depth / y_h / t), as fog.py:227-299.
@@ -178,12 +251,8 @@ class EnhancedFogSynthesizer:
         for i, (gh, gw) in enumerate(shapes):
             f.lat_gh[i], f.lat_gw[i] = gh, gw
         # depth-blur band sizes: int(max(1, 1.5 * mean(r in band))) | 1 with r = depth * depth_blur_max * (0.5 + beta), fog.py:203-213
-        for i, (count, vals) in enumerate(geo["bands"]):
-            rad = 0
-            if count >= 100:
-                r = np.clip(vals * self.depth_blur_max * (0.5 + base_beta), 0.0, self.depth_blur_max * 1.5)
-                rad = int(max(1, np.mean(r) * 1.5)) | 1
-            f.band_rad[i] = rad if rad > 1 else 0
+        for i, rad in enumerate(self._band_radii(geo, base_beta)):
+            f.band_rad[i] = rad
         f.glow_k = int(9 + 20 * glow) | 1
         f.glow_k2 = int(max(7, (h + w) * (0.003 + 0.01 * glow))) | 1
         f.fade_d = int(5 + cdrop * 20) | 1

@@ -128,6 +128,52 @@ def test_host_side_matches_the_reference_draw_for_draw():
         assert abs(meta["A_map"].mean() - fr.a_target) < 0.02           # the airlight map is scaled to this mean, then clipped
 
 
+def test_host_shortcuts_equal_the_plain_formulas():
+    """The per-frame host work is done with less arithmetic than the reference spends (one partition instead of a full quantile,
+    the band radii from per-geometry means) -- the results must be the plain formulas' bit for bit: fog.py:120-131 and :203-213."""
+    from rvb200 import synth
+    from rvb200.augment import EnhancedFogSynthesizer
+    from rvb200.augment import fog as F
+
+    def plain_airlight(rng, bgr):
+        top = bgr[:max(10, int(0.12 * bgr.shape[0]))].astype(np.float32) / 255.0
+        lum = 0.299 * top[:, :, 2] + 0.587 * top[:, :, 1] + 0.114 * top[:, :, 0]
+        mask = lum >= np.quantile(lum, 0.9)
+        a = (top.mean(axis=(0, 1)) if mask.sum() < 100 else top[mask].mean(axis=0)).astype(np.float32)
+        return np.clip(a + rng.uniform(-0.02, 0.02, size=3).astype(np.float32), 0.7, 1.0)
+
+    def plain_radii(dmax, geo, beta):
+        out = []
+        for count, vals in geo["bands"]:
+            rad = 0
+            if count >= 100:
+                r = np.clip(vals * dmax * (0.5 + beta), 0.0, dmax * 1.5)
+                rad = int(max(1, np.mean(r) * 1.5)) | 1
+            out.append(rad if rad > 1 else 0)
+        return out
+
+    rng = np.random.RandomState(4)
+    for (h, w) in [(1080, 1920), (270, 480), (97, 131), (84, 11)]:
+        frames = [synth.clean_scene(h, w, 3), rng.randint(0, 256, (h, w, 3)).astype(np.uint8), np.full((h, w, 3), 200, np.uint8),
+                  rng.randint(100, 104, (h, w, 3)).astype(np.uint8), np.clip(rng.normal(180, 3, (h, w, 3)), 0, 255).astype(np.uint8)]
+        for img in frames:
+            mine = EnhancedFogSynthesizer(seed=3, context=object(), **KW)
+            got, want = mine._airlight_colour(img), plain_airlight(np.random.RandomState(3), img)
+            assert got.dtype == want.dtype and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (h, w)
+        for dmax in (4.0, 3.5, 9.0):
+            kw = dict(KW, depth_blur_max=dmax)
+            mine = EnhancedFogSynthesizer(seed=3, context=object(), **kw)
+            geo = mine._geometry(h, w)
+            for t in range(40):
+                beta = rng.uniform(0.02, 0.25) if t % 4 else 3.912 / rng.uniform(2, 300)      # presets and visibility (mor) values
+                assert mine._band_radii(geo, beta) == plain_radii(dmax, geo, beta), (h, w, dmax, beta)
+    assert F._FAST_QUANTILE is True          # this numpy: the one-partition quantile reproduces np.quantile (else it is not used)
+    for t in range(400):
+        x = [rng.rand(999), rng.randint(0, 5, 1877) / 7.0, 0.5 + np.arange(2500) * 6e-8, rng.normal(0.7, 1e-6, 4001)][t % 4].astype(np.float32)
+        rng.shuffle(x)
+        assert F._quantile09_fast(x) == np.quantile(x, 0.9)
+
+
 def test_fog_has_no_cpu_fallback():
     import rvb200
     from rvb200 import _native
