@@ -1219,7 +1219,7 @@ int rv_create(int device, rv_ctx **out)
     memset(t, 0, sizeof *t);
     memcpy(t->g8, RV_LAB_G8, sizeof RV_LAB_G8);
     memcpy(t->yt, RV_LAB_YT, sizeof RV_LAB_YT);
-    memcpy(t->ft, RV_LAB_FT, sizeof RV_LAB_FT);
+    for (int i = 0; i < 256; ++i) t->ft[i] = (uint16_t)(RV_LAB_FT[i] + RV_LAB_FT_BIAS);     // <= 16384 + 10484
     memcpy(t->cb, RV_LAB_CB, sizeof RV_LAB_CB);
     memcpy(t->ig, RV_LAB_IG, sizeof RV_LAB_IG);
     cudaError_t e = cudaMemcpyToSymbol(g_lab, t, sizeof *t);

@@ -15,6 +15,10 @@ namespace rv {
 // ---------------------------------------------------------------------------------------------
 // LAB tables in global memory (copied into shared memory by the kernels that need them)
 // ---------------------------------------------------------------------------------------------
+// RV_LAB_FT_BIAS: constant carried by every entry of LabTabs::ft (0 = OpenCV's table as it is; 10484 = bdiv's constant, see lab_inv_args_w)
+#ifndef RV_LAB_FT_BIAS
+#define RV_LAB_FT_BIAS 10484           // measured +1.1 % on the LAB kernels (profiles/r2_ak_lab_ft_bias.txt)
+#endif
 struct LabTabs {
     uint16_t g8[256];
     uint16_t yt[256];
@@ -95,9 +99,25 @@ __device__ __forceinline__ int lab_L_fast(const LabHistTabs *t, int B, int G, in
     return t->lq[(t->pm[0][R] + t->pm[1][G] + t->pm[2][B]) >> 12];
 }
 
+// The same from the packed pixel word (B, G, R, x): the three table addresses pm[c] + 4 v come from one byte dot product each (IDP.4A,
+// FMA pipe) and the last look-up takes base + (sum >> 12) as one shift-and-add.  `tabs_s` = shared-memory address of the LabHistTabs.
+__device__ __forceinline__ uint32_t lab_L_px(uint32_t tabs_s, uint32_t px)
+{
+    uint32_t r, g, b, l;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(__dp4a(px, 0x00040000u, tabs_s)));                 // pm[0][R]
+    asm("ld.shared.u32 %0, [%1+1024];" : "=r"(g) : "r"(__dp4a(px, 0x00000400u, tabs_s)));            // pm[1][G]
+    asm("ld.shared.u32 %0, [%1+2048];" : "=r"(b) : "r"(__dp4a(px, 0x00000004u, tabs_s)));            // pm[2][B]
+    asm("ld.shared.u8 %0, [%1+3072];" : "=r"(l) : "r"(tabs_s + ((r + g + b) >> 12)));                // lq[]
+    return l;
+}
+static_assert(offsetof(LabHistTabs, pm) == 0 && offsetof(LabHistTabs, lq) == 3072, "lab_L_px addresses the tables by offset");
+
 // Right shifts of the LAB fixed-point code.  RV_LAB_MULHI = 1 expresses them as the high half of a multiplication by 2^(32-n)
 // (IMAD.HI, FMA pipe) instead of SHF (ALU pipe): in k_chain<LAB,*> the ALU pipe is the busier one.  floor semantics = arithmetic
 // shift for negative values.  Experiment switch; see DESIGN.md for the measurement.
+#ifndef RV_LAB_AB_IMAD
+#define RV_LAB_AB_IMAD 0
+#endif
 #ifndef RV_LAB_MULHI
 #define RV_LAB_MULHI 0
 #endif
@@ -159,8 +179,14 @@ __device__ __forceinline__ void lab_fwd_px2(uint32_t tabs_s, uint32_t px, uint32
     asm("ld.shared.u16 %0, [%1];" : "=r"(fY) : "r"(__dp2a_hi(sy, 0x02000000u, cb_s)));
     asm("ld.shared.u16 %0, [%1];" : "=r"(fZ) : "r"(__dp2a_hi(sz, 0x02000000u, cb_s)));
     accL = 592u * fY - 2641100u;                                              // 2 x (296 fY - 1336934 + 16384) >= 0
+#if RV_LAB_AB_IMAD
+    // the differences as two multiply-adds each (FMA pipe) instead of a subtraction (ALU pipe, the busier one) and a multiply-add
+    a = lab_shr<15>((int)fY * -500 + ((int)fX * 500 + ((128 << 15) + 16384)));
+    bb = lab_shr<15>((int)fZ * -200 + ((int)fY * 200 + ((128 << 15) + 16384)));
+#else
     a = lab_shr<15>(500 * ((int)fX - (int)fY) + ((128 << 15) + 16384));
     bb = lab_shr<15>(200 * ((int)fY - (int)fZ) + ((128 << 15) + 16384));
+#endif
 }
 
 // A.2 inverse arguments from the rounded blend result as it leaves the float unit: Lw = bits of (res + 1.5 * 2^23), i.e. the new L in
@@ -171,10 +197,17 @@ __device__ __forceinline__ void lab_inv_args_w(uint32_t tabs_s, uint32_t Lw, int
     asm("ld.shared.u16 %0, [%1];" : "=r"(yy) : "r"(__dp2a_lo(Lw, 0x00000002u, tabs_s + (uint32_t)offsetof(LabTabs, yt))));
     asm("ld.shared.u16 %0, [%1];" : "=r"(fy) : "r"(__dp2a_lo(Lw, 0x00000002u, tabs_s + (uint32_t)offsetof(LabTabs, ft))));
     y = (int)yy;
+#if RV_LAB_FT_BIAS
+    // the ft table carries + 10484, the constants of adiv and bdiv ride inside the products and -floor(u / 512) is taken as
+    // floor((511 - u) / 512): each argument is one IMAD and one shift-and-add (LEA.HI) instead of IMAD, shift and two adds
+    ix = (int)fy + lab_shr<13>(a * 268435 + (128 - (4194 + RV_LAB_FT_BIAS) * 8192));
+    iz = (int)fy + lab_shr<9>(b * -41943 + (511 - 16));
+#else
     const int adiv = lab_shr<13>(5 * a * 53687 + 128) - 4194;
     const int bdiv = lab_shr<9>(b * 41943 + 16) - 10485 + 1;
     ix = (int)fy + adiv;
     iz = (int)fy - bdiv;
+#endif
 }
 
 __device__ __forceinline__ int lab_xz(int i)
@@ -188,17 +221,34 @@ __device__ __forceinline__ int lab_xz(int i)
 __device__ __forceinline__ void lab_inv_args(const LabTabs *t, int L, int a, int b, int &y, int &ix, int &iz)
 {
     y = t->yt[L];
-    const int fy = t->ft[L];
+    const int fy = t->ft[L] - RV_LAB_FT_BIAS;
     const int adiv = lab_shr<13>(5 * a * 53687 + 128) - 4194;
     const int bdiv = lab_shr<9>(b * 41943 + 16) - 10485 + 1;
     ix = fy + adiv;
     iz = fy - bdiv;
 }
+#ifndef RV_LAB_LEA_IG
+#define RV_LAB_LEA_IG 1                // measured: LAB k3 +3.2 %, LAB k5 +2.4 %, 4K LAB +3.4 % (profiles/r2_aj_lab_lea.txt)
+#endif
 template <bool CUBIC_ONLY>
 __device__ __forceinline__ void lab_inv_tail(const LabTabs *t, int y, int ix, int iz, int &B, int &G, int &R)
 {
     const int x = CUBIC_ONLY ? lab_shr<14>(lab_shr<14>(ix * ix) * ix) : lab_xz(ix);
     const int z = CUBIC_ONLY ? lab_shr<14>(lab_shr<14>(iz * iz) * iz) : lab_xz(iz);
+#if RV_LAB_LEA_IG
+    // clamp BEFORE the shift -- clamp(s >> 14, 0, 4095) == clamp(s, 0, 4095 << 14 | 0x3fff) >> 14 -- so that the shift and the table's
+    // base address fuse into one LEA.HI: VIMNMX.RELU + LEA.HI per channel instead of SHF + VIMNMX.RELU + IADD
+    constexpr int TOP = (4095 << 14) | 0x3fff;
+    const uint32_t ro = (uint32_t)__vimin_s32_relu(12615 * x - 6296 * y - 2223 * z + 8192, TOP);
+    const uint32_t go = (uint32_t)__vimin_s32_relu(-3773 * x + 7684 * y + 185 * z + 8192, TOP);
+    const uint32_t bo = (uint32_t)__vimin_s32_relu(217 * x - 836 * y + 4715 * z + 8192, TOP);
+    const uint32_t ig_s = smem_u32(t) + (uint32_t)offsetof(LabTabs, ig);
+    uint32_t b8, g8v, r8;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(b8) : "r"(ig_s + (bo >> 14)));
+    asm("ld.shared.u8 %0, [%1];" : "=r"(g8v) : "r"(ig_s + (go >> 14)));
+    asm("ld.shared.u8 %0, [%1];" : "=r"(r8) : "r"(ig_s + (ro >> 14)));
+    B = (int)b8; G = (int)g8v; R = (int)r8;
+#else
     int ro = lab_shr<14>(12615 * x - 6296 * y - 2223 * z + 8192);
     int go = lab_shr<14>(-3773 * x + 7684 * y + 185 * z + 8192);
     int bo = lab_shr<14>(217 * x - 836 * y + 4715 * z + 8192);
@@ -208,6 +258,7 @@ __device__ __forceinline__ void lab_inv_tail(const LabTabs *t, int y, int ix, in
     B = t->ig[bo];
     G = t->ig[go];
     R = t->ig[ro];
+#endif
 }
 
 __device__ __forceinline__ void copy_lab_tabs(LabTabs *dst)

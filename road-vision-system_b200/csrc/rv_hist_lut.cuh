@@ -9,6 +9,9 @@
 #ifndef RV_HIST_DP4A
 #define RV_HIST_DP4A 1
 #endif
+#ifndef RV_HIST_LAB16
+#define RV_HIST_LAB16 0                // LAB histograms also take the 16-pixel vector path, table addresses from the packed pixel word (IDP.4A)
+#endif
 
 namespace rv {
 
@@ -63,8 +66,9 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
     const bool interior = (x0 + g.tw <= g.W) && (y1 <= g.H);
     const bool vec_ok = interior && (g.tw % 4 == 0) && (pitch % 4 == 0) &&
                         ((reinterpret_cast<uintptr_t>(frame) & 3) == 0);
-    const bool vec16_ok = vec_ok && SPACE == 0 && !EXTRA && RV_HIST_DP4A && (g.tw % 16 == 0) && (pitch % 16 == 0) &&
+    const bool vec16_ok = vec_ok && (SPACE == 0 || RV_HIST_LAB16) && !EXTRA && RV_HIST_DP4A && (g.tw % 16 == 0) && (pitch % 16 == 0) &&
                           ((reinterpret_cast<uintptr_t>(frame) & 15) == 0);
+    [[maybe_unused]] const uint32_t tabs_s = smem_u32(tabs);
     if (nrows > 0 && vec16_ok) {
         // 16 pixels = 48 bytes = three 16-byte loads per group, two groups in flight per thread; Y straight from the packed
         // words with byte dot products (no unpacking), one shared-memory atomic per pixel
@@ -82,7 +86,10 @@ k_luma_hist(const uint8_t *__restrict__ src, size_t pitch, size_t fstride, Geo g
         auto quad = [&](uint32_t w0, uint32_t w1, uint32_t w2) {
             const uint32_t pp[4] = {w0, __funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 16), w2 >> 8};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) atomicAdd(&myh[luma_y(pp[j])], 1u);
+            for (int j = 0; j < 4; ++j) {
+                if (SPACE == 1) atomicAdd(&myh[lab_L_px(tabs_s, pp[j])], 1u);
+                else atomicAdd(&myh[luma_y(pp[j])], 1u);
+            }
         };
         auto consume = [&](const uint4 (&w)[3]) {
             quad(w[0].x, w[0].y, w[0].z);
