@@ -101,6 +101,12 @@ const char *rv_last_error(const rv_ctx *ctx);
 int rv_set_option(rv_ctx *ctx, const char *name, long value);
 /* kernels launched by this context since creation (for bench accounting) */
 long rv_launch_count(const rv_ctx *ctx);
+
+/* The chunk schedule of the host pipeline (pure host arithmetic, no context, no GPU: for tests and for callers that size their rings):
+ * a job of n frames with at most chunk_frames per chunk; taper != 0 = the default schedule with smaller chunks at both ends (option
+ * "chunk_taper").  Writes the first min(count, cap) chunk sizes to out and returns the number of chunks (RV_ERR_ARG on bad arguments).
+ * No reference counterpart: the reference processes one frame per call (main_preview.py:94). */
+int rv_chunk_schedule(int n, int chunk_frames, int taper, int *out, int cap);
 /* With option "kernel_timing" = 1 every k_luma_hist (which=0), k_build_lut (1) and k_chain (2) launch is
  * bracketed by CUDA events on its own stream; this returns the summed device time and launch count
  * since the last reset (synchronises first). */

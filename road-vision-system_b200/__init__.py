@@ -10,7 +10,7 @@ root (`import rvb200`), or place this directory on a path under an importable na
 drop-in case: as `src` next to main_preview.py).
 """
 from . import _native
-from ._native import kernel_source_hash, kernel_sass_hash, kernel_sass_hashes, Context, DeviceArray, Params, RvError, default_context, library_path, build_library
+from ._native import chunk_schedule, kernel_source_hash, kernel_sass_hash, kernel_sass_hashes, Context, DeviceArray, Params, RvError, default_context, library_path, build_library
 from .preprocess import PreprocessPipeline
 from .preprocess.base import PreprocessOp
 from .preprocess.registry import REGISTRY, get_op_class
@@ -18,7 +18,7 @@ from .preprocess.ops import CLAHEDehaze, MedianDerain
 from .io_video import VideoSource, Frame, FPSMeter, BatchFeeder, SyntheticReader
 
 __all__ = [
-    "kernel_source_hash", "kernel_sass_hash", "kernel_sass_hashes", "Context", "DeviceArray", "Params", "RvError", "default_context", "library_path", "build_library",
+    "chunk_schedule", "kernel_source_hash", "kernel_sass_hash", "kernel_sass_hashes", "Context", "DeviceArray", "Params", "RvError", "default_context", "library_path", "build_library",
     "PreprocessPipeline", "PreprocessOp", "REGISTRY", "get_op_class",
     "CLAHEDehaze", "MedianDerain", "VideoSource", "Frame", "FPSMeter", "BatchFeeder", "SyntheticReader",
 ]

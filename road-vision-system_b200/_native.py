@@ -65,6 +65,17 @@ class DeviceArray:
         return out
 
 
+def chunk_schedule(n, chunk_frames, taper=True):
+    """Chunk sizes the host pipeline cuts a job of n frames into (rv_chunk_schedule; needs the library, not a GPU)."""
+    lib = load_library()
+    cnt = lib.rv_chunk_schedule(n, chunk_frames, 1 if taper else 0, None, 0)
+    if cnt < 0:
+        raise ValueError("bad arguments")
+    out = (C.c_int * max(cnt, 1))()
+    lib.rv_chunk_schedule(n, chunk_frames, 1 if taper else 0, out, cnt)
+    return [int(out[i]) for i in range(cnt)]
+
+
 def library_path():
     return _SO
 
@@ -162,6 +173,7 @@ EXPORTS = {
     "rv_last_error": (C.c_char_p, [C.c_void_p]),
     "rv_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_long]),
     "rv_launch_count": (C.c_long, [C.c_void_p]),
+    "rv_chunk_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "rv_alloc_pinned": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "rv_free_pinned": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rv_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

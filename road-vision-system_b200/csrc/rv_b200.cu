@@ -905,6 +905,20 @@ struct PipeJob {
     int32_t *processed = nullptr;                                               // host, optional
 };
 
+// Frames in chunk number `chunk` of a host job of n frames cut into chunks of at most C, `left` frames still to go (see the comment
+// on the schedule in chain_pipe; rv_chunk_schedule exposes it to the CPU tests).
+long chunk_frames_at(long C, bool taper, long n, int chunk, long left)
+{
+    long want = C;
+    if (taper && C >= 2 && n > 3 * C) {
+        const long Cs = std::max<long>(1, C / 3);
+        if (chunk == 0) want = Cs;
+        else if (chunk == 1) want = std::max<long>(Cs, 2 * C / 3);
+        else if (left > Cs && left <= C + Cs) want = left - Cs;          // the last two chunks: (rest - C/3, C/3)
+    }
+    return std::min<long>(want, left);
+}
+
 int chain_pipe(rv_ctx *ctx, const PipeJob &j, int n, int h, int w, const rv_params *p)
 {
     const long C = std::min<long>(std::min<long>(auto_chunk(ctx, h, w), std::max(1, n)), 4096);
@@ -930,19 +944,11 @@ int chain_pipe(rv_ctx *ctx, const PipeJob &j, int n, int h, int w, const rv_para
     // (C/3, 2C/3, C, ..., C, rest - C/3, C/3) so that both ends of the pipeline fill and drain in a third of the time.  Measured at
     // 64 x 1080p: +0.3 % full frames back, +0.8 % tensor rows back, +0.5 % nothing back (profiles/r2_ac_chunk_taper.jsonl) -- small,
     // because the legs sit at the PCIe link's duplex rate (43 GB/s each way), but consistent and free.
-    const long Cs = std::max<long>(1, C / 3);
-    const bool taper = ctx->chunk_taper != 0 && C >= 2 && n > 3 * C;
+    const bool taper = ctx->chunk_taper != 0;
     int chunk = 0;
     for (int f0 = 0, g = 0; f0 < n; f0 += g, ++chunk) {
         const int s = chunk % NPIPE;
-        const long left = n - f0;
-        long want = C;
-        if (taper) {
-            if (chunk == 0) want = Cs;
-            else if (chunk == 1) want = std::max<long>(Cs, 2 * C / 3);
-            else if (left > Cs && left <= C + Cs) want = left - Cs;      // the last two chunks: (rest - C/3, C/3)
-        }
-        g = (int)std::min<long>(want, left);
+        g = (int)chunk_frames_at(C, taper, n, chunk, n - f0);
         cudaStream_t st = ctx->pipe[s];
         // input
         const uint8_t *di;
@@ -1292,6 +1298,18 @@ int rv_set_option(rv_ctx *ctx, const char *name, long value)
 }
 
 long rv_launch_count(const rv_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int rv_chunk_schedule(int n, int chunk_frames, int taper, int *out, int cap)
+{
+    if (n < 0 || chunk_frames < 1 || (cap > 0 && !out)) return RV_ERR_ARG;
+    int chunk = 0;
+    for (long f0 = 0; f0 < n; ++chunk) {
+        const long g = chunk_frames_at(chunk_frames, taper != 0, n, chunk, n - f0);
+        if (chunk < cap) out[chunk] = (int)g;
+        f0 += g;
+    }
+    return chunk;
+}
 
 int rv_alloc_pinned(rv_ctx *ctx, size_t bytes, void **out)
 {

@@ -115,6 +115,28 @@ def test_video_source_read_and_read_batch():
     assert abs(m.fps - 1.0) < 1e-9
 
 
+def test_host_pipeline_chunk_schedule():
+    """rv_chunk_schedule (the arithmetic chain_pipe cuts host jobs with): chunks partition the job in order, none exceeds the chunk
+    size, the uniform schedule is n // C full chunks and a remainder, the tapered one starts and ends small once the job is longer
+    than three chunks.  Pure host code: runs without a GPU."""
+    import rvb200
+    for C in range(1, 14):
+        for n in list(range(0, 90)) + [127, 128, 1000]:
+            uni, tap = rvb200.chunk_schedule(n, C, taper=False), rvb200.chunk_schedule(n, C, taper=True)
+            for sched in (uni, tap):
+                assert sum(sched) == n and all(1 <= g <= C for g in sched), (n, C, sched)
+            assert uni == [C] * (n // C) + ([n % C] if n % C else [])
+            if C >= 2 and n > 3 * C:
+                small = max(1, C // 3)
+                assert tap[0] == small and tap[1] == max(small, 2 * C // 3) and tap[-1] <= max(small, 1), (n, C, tap)
+                assert len(tap) <= len(uni) + 3
+            else:
+                assert tap == uni
+    assert rvb200.chunk_schedule(64, 3) == [1, 2] + [3] * 20 + [1]          # the benchmark's job: 64 x 1080p frames
+    lib = rvb200._native.load_library()
+    assert lib.rv_chunk_schedule(5, 0, 1, None, 0) < 0 and lib.rv_chunk_schedule(-1, 3, 1, None, 0) < 0
+
+
 def test_median_networks_are_current(tmp_path):
     """The committed rv_median_net.h is what tools/gen_median_net.py generates (networks verified there: random vectors for every
     network, 0-1 vectors at the median threshold for k = 7, 9; the exhaustive 0-1 check of k <= 5 runs without --quick)."""
